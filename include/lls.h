@@ -1,0 +1,230 @@
+/*
+ * liblls — C ABI of the B200-native lifting-line solve path (sm_100a CUDA).
+ *
+ * MachUpX (the reference) has no FFI: its hot path is a set of private numpy methods on
+ * machupX.Scene.  This header is the boundary a maintainer would bind (ctypes, see
+ * INTEGRATION.md) to replace exactly those methods.  Each entry point cites the reference
+ * method it replaces (file:line under the reference tree).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, int return codes (LLS_OK == 0), no exceptions.
+ *   - Every `d_*` pointer is DEVICE memory owned by the caller (the Python host passes
+ *     torch.Tensor.data_ptr()); the library allocates no large buffers itself.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - All floating point data is IEEE double.  Tables are field-major ("SoA"):
+ *       tab[f * ld + i]   f = field index below, i = control-point / horseshoe index, ld >= n.
+ *   - Vectors are stored in earth-fixed AXES but relative to the owning aircraft's origin
+ *     (rotated by the aircraft quaternion, not translated); aircraft origins are in the
+ *     per-aircraft state block, so same-aircraft differences never lose digits to a large
+ *     position offset.
+ */
+#ifndef LLS_H
+#define LLS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return / status codes ------------------------------------------------------------ */
+#define LLS_OK 0
+#define LLS_ERR_CUDA 1
+#define LLS_ERR_ARG 2
+#define LLS_ERR_UNSUPPORTED 3
+#define LLS_ERR_STATE 4
+
+/* status bits written by the solvers (reference: scene.py:622-623, 905-908; common_issues.md:12) */
+#define LLS_STATUS_NOT_CONVERGED 1
+#define LLS_STATUS_IMPINGEMENT 2
+#define LLS_STATUS_NAN 4
+#define LLS_STATUS_SMALL_PIVOT 8
+
+/* ---- solver flags (reference: scene.py:82-87) ------------------------------------------ */
+#define LLS_FLAG_SWEPT_SECTIONS 1
+#define LLS_FLAG_TOTAL_VELOCITY 2
+#define LLS_FLAG_IN_PLANE 4
+#define LLS_FLAG_MATCH_MACHUP_PRO 8
+#define LLS_FLAG_DEFAULT (LLS_FLAG_SWEPT_SECTIONS | LLS_FLAG_TOTAL_VELOCITY | LLS_FLAG_IN_PLANE)
+
+/* ---- per-control-point double table fields --------------------------------------------- */
+enum lls_field {
+    LLS_F_PC = 0,      /* 3: control point (airplane.py:503, scene.py:445-447)                */
+    LLS_F_P0 = 3,      /* 3: inbound node (airplane.py:528)                                   */
+    LLS_F_P1 = 6,      /* 3: outbound node (airplane.py:529)                                  */
+    LLS_F_P0J = 9,     /* 3: inbound plain joint (airplane.py:555)                            */
+    LLS_F_P1J = 12,    /* 3: outbound plain joint (airplane.py:556)                           */
+    LLS_F_PCD = 15,    /* 3: d(PC)/d(span) direction, PC_deriv (airplane.py:564)              */
+    LLS_F_UAU = 18,    /* 3: unswept axial unit vector (airplane.py:537)                      */
+    LLS_F_UNU = 21,    /* 3: unswept normal unit vector (airplane.py:538)                     */
+    LLS_F_UA = 24,     /* 3: section axial vector used by the solver (scene.py:451-458)       */
+    LLS_F_UN = 27,     /* 3: section normal vector                                            */
+    LLS_F_US = 30,     /* 3: section spanwise vector                                          */
+    LLS_F_DL = 33,     /* 3: bound segment P1-P0 (airplane.py:689)                            */
+    LLS_F_RCG = 36,    /* 3: control point relative to CG (airplane.py:561)                   */
+    LLS_F_SPC = 39,    /* control-point span location from the wing's left tip (airplane.py:519) */
+    LLS_F_SP0 = 40,    /* inbound node span location (airplane.py:524)                        */
+    LLS_F_SP1 = 41,    /* outbound node span location (airplane.py:525)                       */
+    LLS_F_SIGMA = 42,  /* blending sigma (airplane.py:513)                                    */
+    LLS_F_CDJ0 = 43,   /* P0 chord * joint length (airplane.py:635)                           */
+    LLS_F_CDJ1 = 44,   /* P1 chord * joint length (airplane.py:647)                           */
+    LLS_F_CBAR = 45,   /* mean chord, already * cos(sweep) if swept sections (scene.py:423-425) */
+    LLS_F_DS = 46,     /* planform area element (wing_segment.py:691)                         */
+    LLS_F_CSWI = 47,   /* 1/cos(section sweep) (scene.py:426); 1 if swept sections are off    */
+    LLS_F_RHO = 48,    /* density at the control point (scene.py:544)                         */
+    LLS_F_NU = 49,     /* kinematic viscosity (scene.py:545)                                  */
+    LLS_F_SOS = 50,    /* speed of sound (scene.py:546)                                       */
+    LLS_F_VWIND = 51,  /* 3: wind at the control point (scene.py:547)                         */
+    LLS_F_WB = 54,     /* spanwise airfoil blend weight d (wing_segment.py:1070)              */
+    LLS_F_FLAP_DA = 55,  /* flap: delta * eps_ideal * eta_hinge * eta_defl   [rad]            */
+    LLS_F_FLAP_DCM = 56, /* flap: delta * (sin 2theta_f - 2 sin theta_f)/4                    */
+    LLS_F_FLAP_DCD = 57, /* flap: 0.002 * |delta| * 180/pi                                    */
+    LLS_F_FLAP_DEFL = 58, /* raw flap deflection [rad] (wing_segment.py:1370-1374)            */
+    LLS_F_FLAP_CF = 59,   /* flap chord fraction (wing_segment.py:656)                        */
+    LLS_NF = 60
+};
+
+/* ---- per-control-point int32 table fields ---------------------------------------------- */
+enum lls_ifield {
+    LLS_I_WING_BEGIN = 0, /* first scene index of the wing (lifting line) holding i (airplane.py:548) */
+    LLS_I_WING_END = 1,   /* one past the last                                                 */
+    LLS_I_AIRCRAFT = 2,   /* aircraft index (scene.py:405-420)                                 */
+    LLS_I_REID = 3,       /* 1 if general-NLL (Reid) corrections are on for i (airplane.py:511) */
+    LLS_I_SEGMENT = 4,    /* scene-wide segment index, for the force sums (scene.py:1102-1117) */
+    LLS_I_AFA = 5,        /* airfoil id of the inboard bracketing airfoil                      */
+    LLS_I_AFB = 6,        /* airfoil id of the outboard bracketing airfoil (== AFA if single)  */
+    LLS_NI = 7
+};
+
+/* ---- airfoil parameter block (one per airfoil id), doubles ------------------------------ */
+enum lls_airfoil_field {
+    LLS_AF_TYPE = 0, /* 0 = linear (airfoil_db "linear") ; 1 = poly_fit                        */
+    LLS_AF_AL0 = 1,
+    LLS_AF_CLA = 2,
+    LLS_AF_CML0 = 3,
+    LLS_AF_CMA = 4,
+    LLS_AF_CD0 = 5,
+    LLS_AF_CD1 = 6,
+    LLS_AF_CD2 = 7,
+    LLS_AF_CLMAX = 8,
+    LLS_AF_STRIDE = 16
+};
+
+/* ---- per-aircraft state block, doubles --------------------------------------------------- */
+enum lls_aircraft_field {
+    LLS_AC_VTRANS = 0, /* 3: -v (earth frame), freestream due to translation (scene.py:565)   */
+    LLS_AC_W = 3,      /* 3: angular rate rotated to earth axes, R^-1(q) w (scene.py:569)     */
+    LLS_AC_POS = 6,    /* 3: earth-fixed position p_bar (scene.py:442)                        */
+    LLS_AC_CGR = 9,    /* 3: CG rotated to earth axes (scene.py:579)                          */
+    LLS_AC_STRIDE = 12
+};
+
+/* ---- per-control-point solution table (outputs), field-major with the same ld ------------ */
+enum lls_out_field {
+    LLS_O_GAMMA = 0,   /* circulation (scene.py:827, 899)                                     */
+    LLS_O_VI = 1,      /* 3: local velocity v_i (scene.py:728)                                */
+    LLS_O_ALPHA = 4,   /* section angle of attack (scene.py:753, 957)                         */
+    LLS_O_CL = 5,      /* section CL incl. sweep correction (scene.py:766, 797)               */
+    LLS_O_CD = 6,      /* section CD (scene.py:1015)                                          */
+    LLS_O_CM = 7,      /* section Cm / cos(sweep) (scene.py:1020, 1026)                       */
+    LLS_O_RE = 8,      /* Reynolds number (scene.py:977)                                      */
+    LLS_O_MACH = 9,    /* Mach number (scene.py:978)                                          */
+    LLS_O_DFINV = 10,  /* 3: inviscid force element (scene.py:952)                            */
+    LLS_O_DMINV = 13,  /* 3: inviscid moment element (scene.py:1036)                          */
+    LLS_O_DFVISC = 16, /* 3: viscous force element (scene.py:1041)                            */
+    LLS_O_DMVISC = 19, /* 3: viscous moment element (scene.py:1046)                           */
+    LLS_O_AL0 = 22,    /* zero-lift angle of the linear pre-pass (scene.py:661)               */
+    LLS_O_REDIM_IP = 23, /* 0.5 rho V_inplane^2 dS (scene.py:987)                             */
+    LLS_O_REDIM_FULL = 24, /* 0.5 rho V^2 dS (scene.py:985)                                   */
+    LLS_O_UTRAIL0 = 25, /* 3: trailing direction at the inbound joint (scene.py:591)          */
+    LLS_O_UTRAIL1 = 28, /* 3: trailing direction at the outbound joint (scene.py:592)         */
+    LLS_O_R = 31,      /* last residual vector (scene.py:723)                                 */
+    LLS_O_VI2 = 32,    /* V_i^2 (scene.py:944)                                                */
+    LLS_NO = 33
+};
+
+typedef struct lls_scene lls_scene; /* opaque */
+
+/* Sizes (bytes) of the caller-provided device buffers for a scene of n control points. */
+typedef struct lls_sizes {
+    size_t ld;           /* padded leading dimension (elements) used by every table/matrix    */
+    size_t tab_bytes;    /* LLS_NF  * ld doubles                                              */
+    size_t itab_bytes;   /* LLS_NI  * ld int32                                                */
+    size_t out_bytes;    /* LLS_NO  * ld doubles                                              */
+    size_t vji_bytes;    /* n * 3 * ld doubles : V[i][c][j]  (scene.py:634 `_V_ji`, component-planar rows) */
+    size_t mat_bytes;    /* n * ld doubles     : A / J, overwritten by its LU factors         */
+    size_t work_bytes;   /* O(n) scratch + LU block inverses                                  */
+} lls_sizes;
+
+int lls_query_sizes(int n, int n_segments, lls_sizes* out);
+
+/* Handle life cycle.  flags = LLS_FLAG_* (reference: scene.py:75-87 solver block). */
+int lls_create(lls_scene** out, int n, int n_aircraft, int n_segments, int n_airfoils, int flags);
+int lls_destroy(lls_scene* h);
+
+/* Bind caller-owned device buffers (sizes from lls_query_sizes). */
+int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab, const double* d_airfoils,
+             double* d_out, double* d_vji, double* d_mat, void* d_work, size_t work_bytes);
+
+/* Per-aircraft flight state, n_aircraft * LLS_AC_STRIDE doubles on the device
+ * (reference: Airplane.set_state airplane.py:105-213 -> scene.py:562-582). */
+int lls_set_state(lls_scene* h, const double* d_ac_state);
+
+/* K-state: freestream at control points and joints, trailing directions, in-plane speeds,
+ * alpha_inf, linear-pass CLa/CL/aL0 with sweep correction.
+ * Replaces the O(N) part of Scene._calc_invariant_flow_properties (scene.py:557-592, 636-666). */
+int lls_flow_state(lls_scene* h, void* stream);
+
+/* K0+K1: horseshoe influence build V_ji = (trail0 + bound + joint0 + joint1 + trail1)/4pi with the
+ * effective-lifting-line (blended, jointed) geometry recomputed per pair in registers.
+ * Replaces Airplane._calculate_geometry effective-LAC loop (airplane.py:569-689),
+ * Scene._perform_geometry_and_atmos_calcs (scene.py:469-541) and the trailing-leg part of
+ * Scene._calc_invariant_flow_properties (scene.py:621-634).
+ * impingement_threshold: scene.py:86.  Sets LLS_STATUS_IMPINGEMENT in the scene status. */
+int lls_build_influence(lls_scene* h, double impingement_threshold, void* stream);
+
+/* K2+K3: assemble A, b and solve A gamma = b.  Replaces Scene._solve_linear (scene.py:800-829)
+ * except its call to _calc_invariant_flow_properties (= lls_flow_state + lls_build_influence). */
+int lls_solve_linear(lls_scene* h, void* stream);
+
+/* K4-K8 + K3: Newton iteration on the lifting-line residual with on-device Jacobian.
+ * Replaces Scene._solve_nonlinear + _lifting_line_residual + _calc_v_i + _get_section_lift
+ * (scene.py:705-797, 832-917).  Host outputs: Newton update count, final ||R||_2, status bits.
+ * err_hist (host, may be NULL) receives the residual norm tested at each iteration (<= max_iter). */
+int lls_solve_nonlinear(lls_scene* h, double convergence, double relaxation, int max_iterations,
+                        void* stream, int* iterations, double* final_error, int* status, double* err_hist);
+
+/* K9+K10: force/moment elements and per-segment sums (earth axes).
+ * d_seg_fm: n_segments * 12 doubles [F_inv(3) M_inv(3) F_visc(3) M_visc(3)].
+ * Replaces the numeric part of Scene._integrate_forces_and_moments (scene.py:941-1046, 1108-1117). */
+int lls_integrate(lls_scene* h, double* d_seg_fm, void* stream);
+
+/* Status bits accumulated since the last lls_flow_state (device flag read back; synchronises). */
+int lls_get_status(lls_scene* h, void* stream, int* status);
+
+/* Dense FP64 LU (no pivoting across blocks; growth/NaN guard) on a row-major n x n matrix with
+ * leading dimension ld, in place, then triangular solves for one right-hand side.
+ * Stands in for numpy.linalg.solve -> LAPACK dgesv at scene.py:827 and scene.py:896. */
+int lls_lu_factor(lls_scene* h, double* d_mat, void* stream);
+int lls_lu_solve(lls_scene* h, const double* d_mat, double* d_rhs_inout, void* stream);
+
+/* Per-phase device timings (ms, CUDA events) of the last lls_solve_nonlinear / lls_solve_linear:
+ * [0] influence build, [1] assembly (A or J, summed), [2] LU factor (summed), [3] triangular solves,
+ * [4] matvec+residual (summed), [5] integrate.  Only filled when timing is enabled. */
+int lls_set_timing(lls_scene* h, int enabled);
+int lls_get_timings(lls_scene* h, double* ms6);
+
+/* FP64 roofline probes: out4 = {DFMA TFLOP/s, DMMA m8n8k4 TFLOP/s, DMMA m16n8k16 TFLOP/s, copy GB/s}. */
+int lls_probe_peaks(double* out4, void* stream);
+
+/* Last error message (thread-local static buffer). */
+const char* lls_last_error(void);
+
+/* ABI version, bumped on any signature or table-layout change. */
+int lls_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLS_H */

@@ -1,0 +1,44 @@
+"""Table layout shared by the host package, the oracle and liblls (mirrors include/lls.h).
+
+The integer constants here MUST match the enums in ``include/lls.h``;
+``tests/test_abi.py`` parses the header and checks every one of them.
+"""
+
+# per-control-point double fields (enum lls_field)
+F_PC, F_P0, F_P1, F_P0J, F_P1J, F_PCD, F_UAU, F_UNU, F_UA, F_UN, F_US, F_DL, F_RCG = (
+    0, 3, 6, 9, 12, 15, 18, 21, 24, 27, 30, 33, 36)
+F_SPC, F_SP0, F_SP1, F_SIGMA, F_CDJ0, F_CDJ1, F_CBAR, F_DS, F_CSWI = 39, 40, 41, 42, 43, 44, 45, 46, 47
+F_RHO, F_NU, F_SOS, F_VWIND = 48, 49, 50, 51
+F_WB, F_FLAP_DA, F_FLAP_DCM, F_FLAP_DCD, F_FLAP_DEFL, F_FLAP_CF = 54, 55, 56, 57, 58, 59
+NF = 60
+
+# per-control-point int32 fields (enum lls_ifield)
+I_WING_BEGIN, I_WING_END, I_AIRCRAFT, I_REID, I_SEGMENT, I_AFA, I_AFB = 0, 1, 2, 3, 4, 5, 6
+NI = 7
+
+# airfoil block (enum lls_airfoil_field)
+AF_TYPE, AF_AL0, AF_CLA, AF_CML0, AF_CMA, AF_CD0, AF_CD1, AF_CD2, AF_CLMAX = 0, 1, 2, 3, 4, 5, 6, 7, 8
+AF_STRIDE = 16
+
+# per-aircraft state block (enum lls_aircraft_field)
+AC_VTRANS, AC_W, AC_POS, AC_CGR = 0, 3, 6, 9
+AC_STRIDE = 12
+
+# per-control-point output fields (enum lls_out_field)
+O_GAMMA, O_VI, O_ALPHA, O_CL, O_CD, O_CM, O_RE, O_MACH = 0, 1, 4, 5, 6, 7, 8, 9
+O_DFINV, O_DMINV, O_DFVISC, O_DMVISC = 10, 13, 16, 19
+O_AL0, O_REDIM_IP, O_REDIM_FULL, O_UTRAIL0, O_UTRAIL1, O_R, O_VI2 = 22, 23, 24, 25, 28, 31, 32
+NO = 33
+
+# solver flags
+FLAG_SWEPT_SECTIONS, FLAG_TOTAL_VELOCITY, FLAG_IN_PLANE, FLAG_MATCH_MACHUP_PRO = 1, 2, 4, 8
+FLAG_DEFAULT = FLAG_SWEPT_SECTIONS | FLAG_TOTAL_VELOCITY | FLAG_IN_PLANE
+
+# status bits
+STATUS_NOT_CONVERGED, STATUS_IMPINGEMENT, STATUS_NAN, STATUS_SMALL_PIVOT = 1, 2, 4, 8
+
+LD_ALIGN = 64  # leading dimension is N rounded up to this many elements
+
+
+def padded_ld(n):
+    return ((int(n) + LD_ALIGN - 1) // LD_ALIGN) * LD_ALIGN
