@@ -221,6 +221,10 @@ int lls_probe_peaks(double* out4, void* stream);
 /* Last error message (thread-local static buffer). */
 const char* lls_last_error(void);
 
+/* Number of CUDA kernels this library has launched since it was loaded (bench.py reports the difference
+ * over its timed region as gpu_launches). */
+unsigned long long lls_launch_count(void);
+
 /* ABI version, bumped on any signature or table-layout change. */
 int lls_abi_version(void);
 

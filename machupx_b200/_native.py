@@ -1,0 +1,72 @@
+"""ctypes binding of liblls (include/lls.h).  The product has NO CPU fallback: if the shared
+library is missing or cannot be loaded this module raises, it never routes anywhere else."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblls.so")
+ABI_VERSION = 1
+
+
+class LlsError(RuntimeError):
+    pass
+
+
+class Sizes(ctypes.Structure):
+    _fields_ = [("ld", ctypes.c_size_t), ("tab_bytes", ctypes.c_size_t), ("itab_bytes", ctypes.c_size_t),
+                ("out_bytes", ctypes.c_size_t), ("vji_bytes", ctypes.c_size_t), ("mat_bytes", ctypes.c_size_t),
+                ("work_bytes", ctypes.c_size_t)]
+
+
+_lib = None
+
+_vp, _i, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+_pi, _pd = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+
+# name -> (restype, argtypes); every symbol include/lls.h declares
+SIGNATURES = {
+    "lls_query_sizes": (_i, [_i, _i, ctypes.POINTER(Sizes)]),
+    "lls_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "lls_destroy": (_i, [_vp]),
+    "lls_bind": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t]),
+    "lls_set_state": (_i, [_vp, _vp]),
+    "lls_flow_state": (_i, [_vp, _vp]),
+    "lls_build_influence": (_i, [_vp, _d, _vp]),
+    "lls_solve_linear": (_i, [_vp, _vp]),
+    "lls_solve_nonlinear": (_i, [_vp, _d, _d, _i, _vp, _pi, _pd, _pi, _pd]),
+    "lls_integrate": (_i, [_vp, _vp, _vp]),
+    "lls_get_status": (_i, [_vp, _vp, _pi]),
+    "lls_lu_factor": (_i, [_vp, _vp, _vp]),
+    "lls_lu_solve": (_i, [_vp, _vp, _vp, _vp]),
+    "lls_set_timing": (_i, [_vp, _i]),
+    "lls_get_timings": (_i, [_vp, _pd]),
+    "lls_probe_peaks": (_i, [_pd, _vp]),
+    "lls_last_error": (ctypes.c_char_p, []),
+    "lls_abi_version": (_i, []),
+    "lls_launch_count": (ctypes.c_ulonglong, []),
+}
+
+
+def load():
+    """Loads liblls.so (built in-tree by build.sh / __graft_entry__.build()) and checks its ABI version."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LlsError("liblls.so not found at {0}: build it with ./build.sh (nvcc, sm_100a). "
+                       "machupx_b200 has no CPU fallback.".format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.lls_abi_version() != ABI_VERSION:
+        raise LlsError("liblls.so ABI version {0} != expected {1}; rebuild".format(lib.lls_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().lls_last_error()
+        raise LlsError("liblls call failed (code {0}): {1}".format(rc, msg.decode() if msg else "?"))

@@ -1,0 +1,263 @@
+// K2, K4-K8: linear-system assembly, induced-velocity matvec fused with the section-lift residual,
+// Jacobian assembly and the Newton update.  All HBM-streaming kernels over V[i][c][j] (24 B/pair).
+//
+//   assemble_linear   A, b of Scene._solve_linear                           scene.py:811-824
+//   residual          _calc_v_i + _lifting_line_residual + _get_section_lift  scene.py:705-797
+//   assemble_jacobian J of Scene._solve_nonlinear                            scene.py:862-893
+//   newton_update     gamma += relaxation * dGamma                            scene.py:899
+#include "lls_internal.h"
+#include "section.cuh"
+
+namespace lls {
+
+// ---------------------------------------------------------------------------------------------
+// linear system rows: g_i = -(V_inf CLa dS)_i u_n_i, diag_i = 2 |v_inf_rot x dl|, b_i     (scene.py:811-824)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) linear_rows_kernel(int n, int ld, int flags, const double* __restrict__ tab, double* __restrict__ W) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double Vref = (flags & LLS_FLAG_IN_PLANE) ? W[(size_t)W_VINF_IP * ld + i] : W[(size_t)W_VINF_MAG * ld + i];
+    const double CLa = W[(size_t)W_CLA0 * ld + i], CL = W[(size_t)W_CL0 * ld + i];
+    const double dS = tab[(size_t)LLS_F_DS * ld + i];
+    const Vec3 un = ld3(tab, ld, LLS_F_UN, i);
+    st3(W, ld, W_G, i, (-(Vref * CLa * dS)) * un);
+    const Vec3 w = cross(ld3(W, ld, W_VIR, i), ld3(tab, ld, LLS_F_DL, i));
+    W[(size_t)W_DIAG * ld + i] = 2.0 * norm(w);
+    W[(size_t)W_RHS * ld + i] = Vref * Vref * dS * CL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// N^2 assembly.  Thread <-> column j (coalesced over V's component planes and over the output row),
+// CTA walks ASM_ROWS rows whose row vectors sit in shared memory.
+//   LINEAR : M_ij = V_ij . g_i + delta_ij diag_i
+//   NEWTON : Vt = V_ij - u_s_j (u_s_j . V_ij)            (projector of the VORTEX j: scene.py:847 broadcasting)
+//            M_ij = ws_i . (Vt x dl_j) - Vt . g_i - cbar_j (Vt . e_i) + delta_ij diag_i     (scene.py:867-893;
+//            np.cross(V_ji, dl) pairs dl with j, c_bar in the CLRe term pairs with j — both as in the reference)
+// Rows n..ld of M are set to the identity so the LU runs on whole blocks.
+// ---------------------------------------------------------------------------------------------
+constexpr int ASM_ROWS = 16;
+
+template <bool NEWTON>
+__global__ void __launch_bounds__(256) assemble_kernel(int n, int ld, int flags, const double* __restrict__ tab,
+                                                       const double* __restrict__ W, const double* __restrict__ V,
+                                                       double* __restrict__ M) {
+    __shared__ double sg[3][ASM_ROWS], sws[3][ASM_ROWS], se[3][ASM_ROWS], sdiag[ASM_ROWS];
+    const int row0 = blockIdx.y * ASM_ROWS;
+    if (threadIdx.x < ASM_ROWS) {
+        const int i = row0 + threadIdx.x;
+        const bool ok = i < n;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            sg[c][threadIdx.x] = ok ? W[(size_t)(W_G + c) * ld + i] : 0.0;
+            sws[c][threadIdx.x] = (ok && NEWTON) ? W[(size_t)(W_WS + c) * ld + i] : 0.0;
+            se[c][threadIdx.x] = (ok && NEWTON) ? W[(size_t)(W_E + c) * ld + i] : 0.0;
+        }
+        sdiag[threadIdx.x] = ok ? W[(size_t)W_DIAG * ld + i] : 1.0;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ld) return;
+    Vec3 us{0, 0, 0}, dl{0, 0, 0};
+    double cbar = 0.0;
+    const bool in_plane = (flags & LLS_FLAG_IN_PLANE) != 0;
+    if (NEWTON && j < n) {
+        us = ld3(tab, ld, LLS_F_US, j);
+        dl = ld3(tab, ld, LLS_F_DL, j);
+        cbar = tab[(size_t)LLS_F_CBAR * ld + j];
+    }
+#pragma unroll 4
+    for (int r = 0; r < ASM_ROWS; ++r) {
+        const int i = row0 + r;
+        if (i >= ld) break;
+        double m;
+        if (i < n) {
+            const double* v = V + (size_t)i * 3 * ld + j;
+            Vec3 vt{v[0], v[(size_t)ld], v[(size_t)2 * ld]};
+            const Vec3 g{sg[0][r], sg[1][r], sg[2][r]};
+            if (NEWTON) {
+                if (in_plane) vt = vt - dot(us, vt) * us;
+                const Vec3 ws{sws[0][r], sws[1][r], sws[2][r]};
+                const Vec3 e{se[0][r], se[1][r], se[2][r]};
+                m = dot(ws, cross(vt, dl)) - dot(vt, g) - cbar * dot(vt, e);
+            } else {
+                m = dot(vt, g);
+            }
+            if (i == j) m += sdiag[r];
+        } else {
+            m = (i == j) ? 1.0 : 0.0;
+        }
+        M[(size_t)i * ld + j] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual: one CTA per control point i.  v_i = v_inf_rot + sum_j V_ij gamma_j (scene.py:728), then the whole
+// section-lift evaluation (scene.py:732-791), R_i (scene.py:723) and the row vectors of the Jacobian.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int flags, const double* __restrict__ tab,
+                                                           const int32_t* __restrict__ itab, const double* __restrict__ af,
+                                                           const double* __restrict__ V, double* __restrict__ W,
+                                                           double* __restrict__ out, double* __restrict__ partial, int vel_only) {
+    const int i = blockIdx.x;
+    const double* gamma = out + (size_t)LLS_O_GAMMA * ld;
+    const double2* v0 = reinterpret_cast<const double2*>(V + (size_t)i * 3 * ld);
+    const double2* v1 = reinterpret_cast<const double2*>(V + (size_t)i * 3 * ld + ld);
+    const double2* v2 = reinterpret_cast<const double2*>(V + (size_t)i * 3 * ld + 2 * (size_t)ld);
+    const double2* g2 = reinterpret_cast<const double2*>(gamma);
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int j = threadIdx.x; j < ld / 2; j += THREADS) {
+        const double2 g = g2[j], a = v0[j], b = v1[j], c = v2[j];
+        sx = fma(a.x, g.x, fma(a.y, g.y, sx));
+        sy = fma(b.x, g.x, fma(b.y, g.y, sy));
+        sz = fma(c.x, g.x, fma(c.y, g.y, sz));
+    }
+    __shared__ double red[3][THREADS / 32];
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    sz = warp_sum(sz);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sx;
+        red[1][threadIdx.x >> 5] = sy;
+        red[2][threadIdx.x >> 5] = sz;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    sx = sy = sz = 0.0;
+    for (int w = 0; w < THREADS / 32; ++w) {
+        sx += red[0][w];
+        sy += red[1][w];
+        sz += red[2][w];
+    }
+    const Vec3 vi = ld3(W, ld, W_VIR, i) + Vec3{sx, sy, sz};                       // scene.py:728
+    if (vel_only) {  // integration pre-pass of a linear solve: only v_i is refreshed (scene.py:943)
+        st3(out, ld, LLS_O_VI, i, vi);
+        return;
+    }
+    const double gam = gamma[i];
+    const Vec3 dl = ld3(tab, ld, LLS_F_DL, i);
+    const Vec3 w = cross(vi, dl);                                                 // scene.py:715-717
+    const double wmag = norm(w);
+    const double L_vortex = 2.0 * wmag * gam;
+    const Vec3 us = ld3(tab, ld, LLS_F_US, i), ua = ld3(tab, ld, LLS_F_UA, i), un = ld3(tab, ld, LLS_F_UN, i);
+    const bool in_plane = flags & LLS_FLAG_IN_PLANE, total = flags & LLS_FLAG_TOTAL_VELOCITY;
+    const bool swept = flags & LLS_FLAG_SWEPT_SECTIONS, pro = flags & LLS_FLAG_MATCH_MACHUP_PRO;
+    const Vec3 vref = in_plane ? (vi - dot(us, vi) * us) : vi;                    // scene.py:737-745
+    const double V2 = dot(vref, vref), Vmag = sqrt(V2);
+    const double cbar = tab[(size_t)LLS_F_CBAR * ld + i], nu = tab[(size_t)LLS_F_NU * ld + i], sos = tab[(size_t)LLS_F_SOS * ld + i];
+    const double Re = Vmag * cbar / nu, Mach = Vmag / sos;
+    const double va = dot(vi, ua), vn = dot(vi, un);                              // scene.py:751-753
+    const double alpha = atan2(vn, va);
+    const SectionParams sp = load_section(tab, itab, af, ld, i);
+    const double CLa = section_CLa(sp);                                           // scene.py:765-768
+    double CL = section_CL(sp, alpha);
+    const double CLRe = section_CLRe(sp, alpha, Re, Mach), CLM = section_CLM(sp, alpha, Re, Mach);
+    const double dS = tab[(size_t)LLS_F_DS * ld + i];
+    const double Vinf = W[(size_t)W_VINF_MAG * ld + i];
+    const double Vfix = in_plane ? W[(size_t)W_VINF_IP * ld + i] : Vinf;
+    double L_section, scale;
+    if (pro) {                                                                    // scene.py:774-775
+        L_section = Vinf * Vinf * CL * dS;
+    } else {
+        if (swept) {                                                              // scene.py:778-779, 797
+            const double aL0 = out[(size_t)LLS_O_AL0 * ld + i];
+            CL += CLa * (aL0 - aL0 * tab[(size_t)LLS_F_CSWI * ld + i]);
+        }
+        L_section = (total ? V2 : Vfix * Vfix) * CL * dS;                         // scene.py:782-791
+    }
+    scale = (total ? V2 : Vfix * Vfix) * dS;                                      // scene.py:881-890
+    const double R = L_vortex - L_section;                                        // scene.py:723
+    // per-control-point results other code reads after a solve
+    st3(out, ld, LLS_O_VI, i, vi);
+    out[(size_t)LLS_O_ALPHA * ld + i] = alpha;
+    out[(size_t)LLS_O_CL * ld + i] = CL;
+    out[(size_t)LLS_O_RE * ld + i] = Re;
+    out[(size_t)LLS_O_MACH * ld + i] = Mach;
+    out[(size_t)LLS_O_R * ld + i] = R;
+    partial[i] = R * R;
+    // Jacobian row data (scene.py:867-893)
+    st3(W, ld, W_WS, i, (2.0 * gam / wmag) * w);
+    const double c2 = total ? 2.0 * dS * CL : 0.0;
+    const double c3 = scale * CLa / (vn * vn + va * va);
+    const double c4 = scale * CLRe / (nu * Vmag), c5 = scale * CLM / (sos * Vmag);
+    st3(W, ld, W_G, i, (c2 + c5) * vref + c3 * (va * un - vn * ua));
+    st3(W, ld, W_E, i, c4 * vref);
+    W[(size_t)W_DIAG * ld + i] = 2.0 * wmag;
+    W[(size_t)W_RHS * ld + i] = -R;                                               // scene.py:896
+}
+
+// deterministic sum of partial[0..n) -> scalars[slot]
+__global__ void __launch_bounds__(256) sum_kernel(int n, const double* __restrict__ partial, double* __restrict__ scalars, int slot) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        scalars[slot] = t;
+    }
+}
+
+__global__ void __launch_bounds__(128) newton_update_kernel(int n, int ld, double relaxation, const double* __restrict__ W, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[(size_t)LLS_O_GAMMA * ld + i] += relaxation * W[(size_t)W_X * ld + i];       // scene.py:899
+}
+
+__global__ void __launch_bounds__(128) copy_gamma_kernel(int n, int ld, const double* __restrict__ W, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[(size_t)LLS_O_GAMMA * ld + i] = W[(size_t)W_X * ld + i];                     // scene.py:827
+}
+
+int launch_assemble_linear(Scene* s, cudaStream_t st) {
+    linear_rows_kernel<<<(s->n + 127) / 128, 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W);
+    count_launch();
+    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS);
+    assemble_kernel<false><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M);
+    count_launch();
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+int launch_residual(Scene* s, int vel_only, cudaStream_t st) {
+    residual_kernel<128><<<s->n, 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial, vel_only);
+    count_launch();
+    if (!vel_only) {
+        sum_kernel<<<1, 256, 0, st>>>(s->n, s->partial, s->scalars, 0);
+        count_launch();
+    }
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+int launch_assemble_jacobian(Scene* s, cudaStream_t st) {
+    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS);
+    assemble_kernel<true><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M);
+    count_launch();
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+int launch_newton_update(Scene* s, double relaxation, cudaStream_t st) {
+    if (relaxation < 0.0) {
+        copy_gamma_kernel<<<(s->n + 127) / 128, 128, 0, st>>>(s->n, s->ld, s->W, s->out);
+        count_launch();
+    } else {
+        newton_update_kernel<<<(s->n + 127) / 128, 128, 0, st>>>(s->n, s->ld, relaxation, s->W, s->out);
+        count_launch();
+    }
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+}  // namespace lls

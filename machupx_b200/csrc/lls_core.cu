@@ -1,13 +1,253 @@
-// Handle, error plumbing and buffer binding of liblls.
+// Handle life cycle, buffer binding and the solver drivers of liblls (the C ABI in include/lls.h).
 #include "lls_internal.h"
 #include <cstring>
+#include <new>
 
 namespace lls {
+
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 void set_last_error(const char* file, int line, const char* msg) {
     snprintf(g_err, sizeof g_err, "%s:%d: %s", file, line, msg);
 }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t work_bytes_for(int ld) {
+    size_t b = 0;
+    b += align_up((size_t)W_NF * ld * 8, 256);
+    b += align_up((size_t)(ld / LU_NB) * 2 * LU_NB * LU_NB * 8, 256);
+    b += align_up((size_t)ld * 8, 256);  // partial
+    b += 256;                            // scalars
+    b += 256;                            // status
+    return b;
+}
+
+struct PhaseTimer {
+    Scene* s;
+    cudaStream_t st;
+    int slot;
+    PhaseTimer(Scene* s_, cudaStream_t st_, int slot_) : s(s_), st(st_), slot(slot_) {
+        if (s->timing) cudaEventRecord(s->ev[0], st);
+    }
+    ~PhaseTimer() {
+        if (s->timing) {
+            cudaEventRecord(s->ev[1], st);
+            cudaEventSynchronize(s->ev[1]);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+            s->ms[slot] += ms;
+        }
+    }
+};
+
+static int read_scalars(Scene* s, cudaStream_t st, int count) {
+    LLS_CUDA_TRY(cudaMemcpyAsync(s->h_pinned, s->scalars, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    LLS_CUDA_TRY(cudaStreamSynchronize(st));
+    return LLS_OK;
+}
+
 }  // namespace lls
+
+using namespace lls;
 
 extern "C" const char* lls_last_error(void) { return lls::g_err; }
 extern "C" int lls_abi_version(void) { return 1; }
+extern "C" unsigned long long lls_launch_count(void) { return lls::g_launches; }
+
+extern "C" int lls_query_sizes(int n, int n_segments, lls_sizes* out) {
+    LLS_REQUIRE(n > 0 && out != nullptr, LLS_ERR_ARG, "lls_query_sizes: bad arguments");
+    (void)n_segments;
+    const size_t ld = align_up((size_t)n, LD_ALIGN);
+    out->ld = ld;
+    out->tab_bytes = (size_t)LLS_NF * ld * 8;
+    out->itab_bytes = (size_t)LLS_NI * ld * 4;
+    out->out_bytes = (size_t)LLS_NO * ld * 8;
+    out->vji_bytes = (size_t)n * 3 * ld * 8;
+    out->mat_bytes = ld * ld * 8;
+    out->work_bytes = work_bytes_for((int)ld);
+    return LLS_OK;
+}
+
+extern "C" int lls_create(lls_scene** out, int n, int n_aircraft, int n_segments, int n_airfoils, int flags) {
+    LLS_REQUIRE(out != nullptr && n > 0 && n_aircraft > 0 && n_segments > 0 && n_airfoils > 0, LLS_ERR_ARG, "lls_create: bad arguments");
+    const bool total = flags & LLS_FLAG_TOTAL_VELOCITY, pro = flags & LLS_FLAG_MATCH_MACHUP_PRO;
+    LLS_REQUIRE(total || pro, LLS_ERR_UNSUPPORTED,
+                "use_total_velocity=False without match_machup_pro is not supported (the reference itself fails there: scene.py:959)");
+    lls_scene* h = new (std::nothrow) lls_scene();
+    LLS_REQUIRE(h != nullptr, LLS_ERR_ARG, "lls_create: out of host memory");
+    h->n = n;
+    h->ld = (int)align_up((size_t)n, LD_ALIGN);
+    h->n_ac = n_aircraft;
+    h->n_seg = n_segments;
+    h->n_af = n_airfoils;
+    h->flags = flags;
+    if (cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) != cudaSuccess || cudaEventCreate(&h->ev[0]) != cudaSuccess ||
+        cudaEventCreate(&h->ev[1]) != cudaSuccess) {
+        set_last_error(__FILE__, __LINE__, "lls_create: CUDA resource creation failed (is a GPU visible?)");
+        delete h;
+        return LLS_ERR_CUDA;
+    }
+    *out = h;
+    return LLS_OK;
+}
+
+extern "C" int lls_destroy(lls_scene* h) {
+    if (h == nullptr) return LLS_OK;
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->ev[0]) cudaEventDestroy(h->ev[0]);
+    if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+    delete h;
+    return LLS_OK;
+}
+
+extern "C" int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab, const double* d_airfoils, double* d_out,
+                        double* d_vji, double* d_mat, void* d_work, size_t work_bytes) {
+    LLS_REQUIRE(h != nullptr, LLS_ERR_ARG, "lls_bind: null handle");
+    LLS_REQUIRE(d_tab && d_itab && d_airfoils && d_out && d_vji && d_mat && d_work, LLS_ERR_ARG, "lls_bind: null buffer");
+    LLS_REQUIRE(work_bytes >= work_bytes_for(h->ld), LLS_ERR_ARG, "lls_bind: work buffer too small");
+    LLS_REQUIRE(((uintptr_t)d_vji % 16 == 0) && ((uintptr_t)d_mat % 16 == 0) && ((uintptr_t)d_out % 16 == 0) && ((uintptr_t)d_work % 256 == 0),
+                LLS_ERR_ARG, "lls_bind: buffers must be 16-byte (work: 256-byte) aligned");
+    h->tab = d_tab;
+    h->itab = d_itab;
+    h->af = d_airfoils;
+    h->out = d_out;
+    h->V = d_vji;
+    h->M = d_mat;
+    char* p = (char*)d_work;
+    h->W = (double*)p;
+    p += align_up((size_t)W_NF * h->ld * 8, 256);
+    h->inv = (double*)p;
+    p += align_up((size_t)(h->ld / LU_NB) * 2 * LU_NB * LU_NB * 8, 256);
+    h->partial = (double*)p;
+    p += align_up((size_t)h->ld * 8, 256);
+    h->scalars = (double*)p;
+    p += 256;
+    h->status = (int*)p;
+    return LLS_OK;
+}
+
+extern "C" int lls_set_state(lls_scene* h, const double* d_ac_state) {
+    LLS_REQUIRE(h != nullptr && d_ac_state != nullptr, LLS_ERR_ARG, "lls_set_state: null argument");
+    h->ac = d_ac_state;
+    return LLS_OK;
+}
+
+#define LLS_CHECK_BOUND(h)                                                                     \
+    LLS_REQUIRE((h) != nullptr && (h)->tab != nullptr && (h)->ac != nullptr, LLS_ERR_STATE,     \
+                "scene is not bound (call lls_bind and lls_set_state first)")
+
+extern "C" int lls_flow_state(lls_scene* h, void* stream) {
+    LLS_CHECK_BOUND(h);
+    return launch_flow_state(h, (cudaStream_t)stream);
+}
+
+extern "C" int lls_build_influence(lls_scene* h, double impingement_threshold, void* stream) {
+    LLS_CHECK_BOUND(h);
+    PhaseTimer t(h, (cudaStream_t)stream, 0);
+    return launch_influence(h, impingement_threshold, (cudaStream_t)stream);
+}
+
+extern "C" int lls_solve_linear(lls_scene* h, void* stream) {
+    LLS_CHECK_BOUND(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        PhaseTimer t(h, st, 1);
+        LLS_TRY(launch_assemble_linear(h, st));
+    }
+    {
+        PhaseTimer t(h, st, 2);
+        LLS_TRY(lu_factor_solve(h, h->M, wf(h, W_RHS), wf(h, W_X), st));
+    }
+    return launch_newton_update(h, -1.0, st);  // gamma = x
+}
+
+extern "C" int lls_solve_nonlinear(lls_scene* h, double convergence, double relaxation, int max_iterations, void* stream,
+                                   int* iterations, double* final_error, int* status, double* err_hist) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(iterations && final_error && status, LLS_ERR_ARG, "lls_solve_nonlinear: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    int it = 0;
+    double error = 100.0;                                                        // scene.py:851-852
+    int flags_out = 0;
+    while (error > convergence) {                                                // scene.py:853
+        ++it;
+        {
+            PhaseTimer t(h, st, 4);
+            LLS_TRY(launch_residual(h, 0, st));                                  // scene.py:857
+        }
+        LLS_TRY(read_scalars(h, st, 1));
+        error = sqrt(h->h_pinned[0]);                                            // scene.py:858
+        if (err_hist) err_hist[it - 1] = error;
+        if (!(error == error)) {  // NaN: the reference's while-test fails on NaN and falls out of the loop
+            flags_out |= LLS_STATUS_NAN;
+        }
+        {
+            PhaseTimer t(h, st, 1);
+            LLS_TRY(launch_assemble_jacobian(h, st));                            // scene.py:862-893
+        }
+        {
+            PhaseTimer t(h, st, 2);
+            LLS_TRY(lu_factor_solve(h, h->M, wf(h, W_RHS), wf(h, W_X), st));     // scene.py:896
+        }
+        LLS_TRY(launch_newton_update(h, relaxation, st));                        // scene.py:899
+        if (it >= max_iterations) {                                              // scene.py:905-908
+            flags_out |= LLS_STATUS_NOT_CONVERGED;
+            break;
+        }
+    }
+    {
+        PhaseTimer t(h, st, 4);
+        LLS_TRY(launch_residual(h, 0, st));                                      // scene.py:906-907, 912-913
+    }
+    LLS_TRY(read_scalars(h, st, 1));
+    *final_error = sqrt(h->h_pinned[0]);
+    *iterations = it;
+    int dev_status = 0;
+    LLS_CUDA_TRY(cudaMemcpyAsync(&dev_status, h->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LLS_CUDA_TRY(cudaStreamSynchronize(st));
+    *status = flags_out | dev_status;
+    return LLS_OK;
+}
+
+extern "C" int lls_integrate(lls_scene* h, double* d_seg_fm, void* stream) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(d_seg_fm != nullptr, LLS_ERR_ARG, "lls_integrate: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    PhaseTimer t(h, st, 5);
+    if (h->flags & LLS_FLAG_MATCH_MACHUP_PRO) LLS_TRY(launch_scale_gamma_pro(h, st));   // scene.py:938-939
+    LLS_TRY(launch_residual(h, 1, st));                                          // v_i with the final gamma, scene.py:943
+    return launch_integrate(h, d_seg_fm, st);
+}
+
+extern "C" int lls_get_status(lls_scene* h, void* stream, int* status) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(status != nullptr, LLS_ERR_ARG, "lls_get_status: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    LLS_CUDA_TRY(cudaMemcpyAsync(status, h->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LLS_CUDA_TRY(cudaStreamSynchronize(st));
+    return LLS_OK;
+}
+
+extern "C" int lls_lu_factor(lls_scene* h, double* d_mat, void* stream) {
+    LLS_REQUIRE(h != nullptr && h->inv != nullptr && d_mat != nullptr, LLS_ERR_STATE, "lls_lu_factor: scene not bound");
+    return lu_factor_solve(h, d_mat, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int lls_lu_solve(lls_scene* h, const double* d_mat, double* d_rhs_inout, void* stream) {
+    LLS_REQUIRE(h != nullptr && h->inv != nullptr && d_mat != nullptr && d_rhs_inout != nullptr, LLS_ERR_STATE, "lls_lu_solve: scene not bound");
+    return lu_solve_only(h, d_mat, d_rhs_inout, (cudaStream_t)stream);
+}
+
+extern "C" int lls_set_timing(lls_scene* h, int enabled) {
+    LLS_REQUIRE(h != nullptr, LLS_ERR_ARG, "null handle");
+    h->timing = enabled != 0;
+    for (double& m : h->ms) m = 0.0;
+    return LLS_OK;
+}
+
+extern "C" int lls_get_timings(lls_scene* h, double* ms6) {
+    LLS_REQUIRE(h != nullptr && ms6 != nullptr, LLS_ERR_ARG, "null argument");
+    for (int i = 0; i < 6; ++i) ms6[i] = h->ms[i];
+    return LLS_OK;
+}

@@ -1,7 +1,8 @@
-// Internal helpers shared by the CUDA translation units of liblls (not part of the C ABI).
+// Internal declarations shared by the CUDA translation units of liblls (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdint>
 #include "../../include/lls.h"
 
 #define LLS_CUDA_TRY(expr)                                                                    \
@@ -13,6 +14,87 @@
         }                                                                                     \
     } while (0)
 
+#define LLS_REQUIRE(cond, code, msg)                                                          \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            lls::set_last_error(__FILE__, __LINE__, msg);                                     \
+            return code;                                                                      \
+        }                                                                                     \
+    } while (0)
+
+#define LLS_TRY(expr)                                                                         \
+    do {                                                                                      \
+        int _rc = (expr);                                                                     \
+        if (_rc != LLS_OK) return _rc;                                                        \
+    } while (0)
+
 namespace lls {
+
 void set_last_error(const char* file, int line, const char* msg);
-}
+extern unsigned long long g_launches;  // kernels launched by this library since load (bench.py's gpu_launches)
+inline void count_launch(int k = 1) { g_launches += (unsigned long long)k; }
+
+constexpr int LD_ALIGN = 64;   // leading dimension granularity (elements); equals the LU block size
+constexpr int LU_NB = 64;      // LU block size
+
+// Per-control-point scratch ("row state"), field-major with the scene's ld.  Produced by the
+// flow-state and residual kernels, consumed by the assembly kernels.
+enum WField {
+    W_VINF = 0,      // 3  v_inf                         (scene.py:571)
+    W_VIR = 3,       // 3  v_inf_and_rot                 (scene.py:572)
+    W_VINF_MAG = 6,  //    |v_inf|                       (scene.py:585)
+    W_VIR_MAG = 7,   //    |v_inf_and_rot|               (scene.py:587)
+    W_VINF_IP = 8,   //    |P v_inf|                     (scene.py:639)
+    W_CLA0 = 9,      //    CLa of the linear pre-pass    (scene.py:659)
+    W_CL0 = 10,      //    CL of the linear pre-pass incl. sweep correction (scene.py:660, 666)
+    W_RHS = 11,      //    right-hand side / Newton step (scene.py:818, 896)
+    W_DIAG = 12,     //    diagonal addend               (scene.py:824, 893)
+    W_G = 13,        // 3  row vector g_i of the assembly kernels
+    W_WS = 16,       // 3  scaled w_i (2 gamma_i/|w_i|) w_i   (scene.py:867)
+    W_E = 19,        // 3  CLRe row vector (scene.py:873)
+    W_X = 22,        //    solution of the triangular solves
+    W_UINF = 23,     // 3  v_inf / |v_inf|               (scene.py:586)
+    W_NF = 26
+};
+
+struct Scene {
+    int n = 0, ld = 0, n_ac = 0, n_seg = 0, n_af = 0, flags = 0;
+    const double* tab = nullptr;
+    const int32_t* itab = nullptr;
+    const double* af = nullptr;
+    const double* ac = nullptr;
+    double* out = nullptr;
+    double* V = nullptr;
+    double* M = nullptr;
+    // carved from the caller's work buffer
+    double* W = nullptr;        // W_NF * ld
+    double* inv = nullptr;      // (ld / LU_NB) * 2 * LU_NB * LU_NB   inverse diagonal blocks (L then U)
+    double* partial = nullptr;  // reduction scratch (>= 4096 doubles)
+    double* scalars = nullptr;  // [0] ||R||^2  [1] min |pivot| ...   (device)
+    int* status = nullptr;      // device status word
+    double* h_pinned = nullptr; // pinned host mirror for scalar read-back (8 doubles)
+    bool timing = false;
+    double ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+inline const double* tabf(const Scene* s, int f) { return s->tab + (size_t)f * s->ld; }
+inline const int32_t* itabf(const Scene* s, int f) { return s->itab + (size_t)f * s->ld; }
+inline double* outf(const Scene* s, int f) { return s->out + (size_t)f * s->ld; }
+inline double* wf(const Scene* s, int f) { return s->W + (size_t)f * s->ld; }
+
+// kernels' host launchers (each returns LLS_OK or an error code)
+int launch_flow_state(Scene* s, cudaStream_t st);
+int launch_influence(Scene* s, double impingement_threshold, cudaStream_t st);
+int launch_assemble_linear(Scene* s, cudaStream_t st);
+int launch_residual(Scene* s, int vel_only, cudaStream_t st);  // matvec + section lift + R, ||R||^2 -> scalars[0]
+int launch_assemble_jacobian(Scene* s, cudaStream_t st);
+int launch_newton_update(Scene* s, double relaxation, cudaStream_t st);
+int launch_integrate(Scene* s, double* d_seg_fm, cudaStream_t st);
+int launch_scale_gamma_pro(Scene* s, cudaStream_t st);
+int lu_factor_solve(Scene* s, double* d_mat, double* d_rhs, double* d_x, cudaStream_t st);  // rhs may be null
+int lu_solve_only(Scene* s, const double* d_mat, double* d_rhs_inout, cudaStream_t st);
+
+}  // namespace lls
+
+struct lls_scene : lls::Scene {};

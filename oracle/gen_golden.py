@@ -110,6 +110,19 @@ def _cases():
     return cases
 
 
+def _big_cases():
+    """Full-size configs of BASELINE.json (tables + reference results only; no V_ji rows).  Slow: minutes."""
+    cases = {}
+    d = os.path.join(REF, "examples/Traditional")
+    c = _embed(_load_json(os.path.join(d, "traditional_input.json")), d)
+    c.pop("run", None)
+    c["solver"]["type"] = "nonlinear"
+    for w in next(iter(c["scene"]["aircraft"].values()))["file"]["wings"].values():
+        w.setdefault("grid", {})["N"] = 800
+    cases["c2_traditional_n4000"] = c     # BASELINE.json configs[1]
+    return cases
+
+
 def _solver_params(inp):
     s = inp.get("solver", {})
     return {"type": s.get("type", "nonlinear"), "convergence": s.get("convergence", 1e-10),
@@ -129,40 +142,54 @@ def _run_reference(inp):
     return scene, FM, hist
 
 
-def generate(name, inp, check=True):
+def generate(name, inp, check=True, lean=False):
     scene, FM, hist = _run_reference(inp)
     tables = build_tables(scene)
     ac_state = build_aircraft_state(scene)
     n = tables["n"]
     sp = _solver_params(inp)
 
-    # the reference's linear solution (re-run the linear solver on a fresh copy of the state)
-    V_ref = scene._V_ji.copy()
+    # snapshot what the nonlinear solve left behind before anything else touches the scene
+    V_ref = scene._V_ji
     gamma = scene._gamma.copy()
-    scene_lin = MX.Scene(copy.deepcopy(inp))
-    scene_lin._solver_type = "linear"
-    scene_lin.solve_forces()
-    gamma_lin = scene_lin._gamma.copy()
+    snap = {k: np.array(getattr(scene, "_" + k)) for k in
+            ("v_i", "alpha", "CL", "CD", "Cm", "Re", "M", "dF_inv", "dM_inv", "dF_visc", "dM_visc", "u_trailing_0", "u_trailing_1")}
+    n_pre = tables["n"]
+    rows_pre = sorted(set([0, 1, n_pre // 4, n_pre // 2 - 1, n_pre // 2, n_pre - 2, n_pre - 1]))
+    V_rows = V_ref[rows_pre].copy()
+    V_stats = {"V_rowsum": V_ref.sum(axis=1), "V_colsum": V_ref.sum(axis=0), "V_abs_sum": np.abs(V_ref).sum(),
+               "V_diag": V_ref[np.arange(n_pre), np.arange(n_pre)].copy()}
+    # the reference's linear solution
+    if lean:
+        scene._solver_type = "linear"
+        scene.solve_forces()
+        gamma_lin = scene._gamma.copy()
+    else:
+        scene_lin = MX.Scene(copy.deepcopy(inp))
+        scene_lin._solver_type = "linear"
+        scene_lin.solve_forces()
+        gamma_lin = scene_lin._gamma.copy()
 
     rows = sorted(set([0, 1, n // 4, n // 2 - 1, n // 2, n - 2, n - 1]))
     gold = {
         "tab": tables["tab"], "itab": tables["itab"], "airfoils": tables["airfoils"], "ac_state": ac_state,
         "n": n, "ld": tables["ld"], "n_aircraft": tables["n_aircraft"], "n_segments": tables["n_segments"],
         "flags": tables["flags"],
-        "V_rows_idx": np.array(rows), "V_rows": V_ref[rows],
-        "V_rowsum": V_ref.sum(axis=1), "V_colsum": V_ref.sum(axis=0), "V_abs_sum": np.abs(V_ref).sum(),
-        "V_diag": V_ref[np.arange(n), np.arange(n)],
+        "V_rows_idx": np.array(rows), "V_rows": V_rows,
         "gamma_linear": gamma_lin, "gamma": gamma, "error_history": np.array(hist),
-        "v_i": scene._v_i, "alpha": scene._alpha, "CL": scene._CL, "CD": scene._CD, "Cm": scene._Cm,
-        "Re": scene._Re, "M": scene._M, "dF_inv": scene._dF_inv, "dM_inv": scene._dM_inv,
-        "dF_visc": scene._dF_visc, "dM_visc": scene._dM_visc,
-        "u_trailing_0": scene._u_trailing_0, "u_trailing_1": scene._u_trailing_1,
     }
+    gold.update(V_stats)
+    gold.update(snap)
+    if lean:
+        for k in ("V_colsum", "dM_inv", "dM_visc", "dF_visc", "u_trailing_0", "u_trailing_1"):
+            gold.pop(k)
+        gold["V_rows_idx"] = np.array(rows[:3])
+        gold["V_rows"] = V_rows[:3]
     meta = {"input": inp, "solver": sp, "FM": FM, "iterations": len(hist),
             "segment_names": [list(x) for x in tables["segment_names"]],
             "reference": "usuaero/MachUpX v2.7.2 + oracle/ref_stubs", "n": n}
 
-    if check:
+    if check and not lean:
         T = O.Tables(tables, ac_state)
         res = O.solve(T, solver_type=sp["type"], convergence=sp["convergence"], relaxation=sp["relaxation"],
                       max_iterations=sp["max_iterations"])
@@ -185,6 +212,10 @@ def generate(name, inp, check=True):
 if __name__ == "__main__":
     os.chdir(REF)  # the reference resolves relative "file" paths against the CWD
     only = sys.argv[1:]
+    for cname, cinp in _big_cases().items():
+        if cname in only:
+            print("generating", cname)
+            generate(cname, cinp, lean=True)
     for cname, cinp in _cases().items():
         if only and cname not in only:
             continue

@@ -303,9 +303,28 @@ def influence_rows(T, F, i0, i1, want_denoms=False):
         d1 = r1jm * (r1jm - np.einsum('ijk,ijk->ij', F.u_trailing_1[None], r1j))
         V1 = np.where(d1[..., None] > 1e-13, np.nan_to_num(np.cross(F.u_trailing_1[None], r1j) / d1[..., None]), 0.0)
         V = FOUR_PI_INV * (V0 + (Vb + Vj0 + Vj1) + V1)                         # scene.py:541, 634
+    if want_denoms == "conditioning":
+        # |dV/V| amplification of the two trailing legs: r (r - u.r) cancels when the control point lies
+        # almost exactly downstream of a joint.  Used by the parity tests to scale their tolerance.
+        with np.errstate(divide='ignore', invalid='ignore'):
+            k0 = np.where(d0 > 1e-13, r0jm * r0jm / d0, 0.0)
+            k1 = np.where(d1 > 1e-13, r1jm * r1jm / d1, 0.0)
+        amp = FOUR_PI_INV * (np.abs(V0).max(axis=-1) * k0 + np.abs(V1).max(axis=-1) * k1)
+        return V, amp
     if want_denoms:
         return V, np.minimum(np.abs(d0).min(), np.abs(d1).min())
     return V
+
+
+def influence_with_conditioning(T, F, block=256):
+    """(V, amp): amp[i, j] bounds how strongly one ulp of input perturbation shows in |V[i, j, :]|."""
+    n = T.n
+    V = np.empty((n, n, 3))
+    amp = np.empty((n, n))
+    for i0 in range(0, n, block):
+        i1 = min(n, i0 + block)
+        V[i0:i1], amp[i0:i1] = influence_rows(T, F, i0, i1, want_denoms="conditioning")
+    return V, amp
 
 
 def influence(T, F, block=256, impingement_threshold=None):

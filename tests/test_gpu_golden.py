@@ -1,0 +1,104 @@
+"""GPU parity: liblls (through the C ABI) against the golden vectors of the unmodified reference."""
+import numpy as np
+import pytest
+
+from golden_utils import CASES, load, segment_sums
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10  # BASELINE.json north_star: circulation and coefficients within 1e-10 relative
+
+
+def _run(name):
+    from machupx_b200.device import DeviceScene
+    tables, ac_state, g, meta = load(name)
+    dev = DeviceScene(tables)
+    dev.upload_state(ac_state)
+    dev.flow_state()
+    dev.build_influence(1e-10)
+    sp = meta["solver"]
+    dev.solve_linear()
+    gamma_lin = dev.gamma()
+    res = {"gamma_linear": gamma_lin, "iterations": 0, "history": []}
+    if sp["type"] == "nonlinear":
+        it, err, status, hist = dev.solve_nonlinear(sp["convergence"], sp["relaxation"], sp["max_iterations"])
+        res.update(iterations=it, error=err, status=status, history=hist)
+    res["seg_fm"] = dev.integrate()
+    res["gamma"] = dev.gamma()
+    res["dev"] = dev
+    return tables, g, meta, res
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_influence_matrix(name):
+    """Every entry of V_ji against the oracle (itself pinned to the reference at 0 ulp on these scenes).
+
+    Tolerance: 1e-11 of the largest entry, plus 4e-13 x the conditioning of the trailing-leg formula
+    r (r - u.r) (scene.py:621), which loses digits when a control point sits almost exactly downstream
+    of a joint (the test aeroplane's fin does, by ~0.005 ft).  The 1e-11 floor covers the joint direction
+    next to a kink of the lifting line (winglet junction): the reference differences a cumulative arc
+    length (airplane.py:627-628), whose own rounding noise (~1e-13 relative in h) turns the tangent there;
+    see DESIGN.md "conditioning".  Circulation and forces are still held to 1e-10 below."""
+    from machupx_b200.device import DeviceScene
+    from oracle import lls_oracle as O
+    tables, ac_state, g, meta = load(name)
+    dev = DeviceScene(tables)
+    dev.upload_state(ac_state)
+    dev.flow_state()
+    dev.build_influence(1e-10)
+    V = dev.V_ji()
+    T = O.Tables(tables, ac_state)
+    Vo, amp = O.influence_with_conditioning(T, O.flow_state(T))
+    scale = np.abs(Vo).max()
+    rows = g["V_rows_idx"]
+    assert np.abs(Vo[rows] - g["V_rows"]).max() / scale < 1e-12       # oracle == reference on the stored rows
+    err = np.abs(V - Vo).max(axis=-1)
+    tol = 1e-11 * scale + 4e-13 * amp
+    worst = np.unravel_index(np.argmax(err - tol), err.shape)
+    assert (err <= tol).all(), "V_ji[%d,%d]: err %.3e tol %.3e" % (worst[0], worst[1], err[worst], tol[worst])
+    n = tables["n"]
+    assert (V[np.arange(n), np.arange(n)] == 0.0).all() or np.abs(V[np.arange(n), np.arange(n)] - g["V_diag"]).max() / scale < 1e-12
+    # padded columns of the device layout must be exactly zero
+    if dev.ld > n:
+        assert float(dev.d_V[:, :, n:].abs().max().item()) == 0.0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_solve_matches_reference(name):
+    tables, g, meta, res = _run(name)
+    gs = np.abs(g["gamma"]).max()
+    assert np.abs(res["gamma_linear"] - g["gamma_linear"]).max() / np.abs(g["gamma_linear"]).max() < RTOL
+    assert np.abs(res["gamma"] - g["gamma"]).max() / gs < RTOL
+    if meta["solver"]["type"] == "nonlinear":
+        assert abs(res["iterations"] - meta["iterations"]) <= 1   # north_star: identical count within one step
+        assert res["iterations"] == meta["iterations"]
+        hist_ref = g["error_history"]
+        for a, b in zip(res["history"], hist_ref):
+            assert abs(a - b) <= 1e-6 * max(b, 1e-9) + 1e-11
+    ref = segment_sums(g, tables)
+    scale = np.abs(ref).max()
+    assert np.abs(res["seg_fm"] - ref).max() / scale < RTOL
+    out = res["dev"].out()
+    from machupx_b200 import layout as L
+    for key, f in (("alpha", L.O_ALPHA), ("CD", L.O_CD), ("Cm", L.O_CM), ("Re", L.O_RE), ("M", L.O_MACH)):
+        assert np.abs(out[f] - g[key]).max() <= RTOL * max(1.0, np.abs(g[key]).max()), key
+    # v_i inherits the conditioning of the trailing-leg entries it sums (see test_influence_matrix)
+    from oracle import lls_oracle as O
+    T = O.Tables(tables, load(name)[1])
+    _, amp = O.influence_with_conditioning(T, O.flow_state(T))
+    tol_vi = RTOL * np.abs(g["v_i"]).max() + 4e-12 * (amp @ np.abs(g["gamma"]))
+    assert (np.abs(out[L.O_VI:L.O_VI + 3].T - g["v_i"]).max(axis=1) <= tol_vi).all()
+
+
+def test_lu_against_lapack():
+    """The device LU on a lifting-line-like matrix against numpy.linalg.solve (LAPACK dgesv, scene.py:827)."""
+    from machupx_b200.device import DeviceScene
+    tables, ac_state, g, meta = load("testplane_nonlinear")
+    dev = DeviceScene(tables)
+    n = tables["n"]
+    rng = np.random.default_rng(7)
+    A = rng.normal(size=(n, n)) * 0.1 + np.diag(5.0 + rng.random(n))
+    b = rng.normal(size=n)
+    x, _ = dev.lu_solve_dense(A, b)
+    xr = np.linalg.solve(A, b)
+    assert np.abs(x - xr).max() / np.abs(xr).max() < 1e-12
