@@ -180,6 +180,13 @@ def generate(name, inp, check=True, lean=False):
     }
     gold.update(V_stats)
     gold.update(snap)
+    if name == "testplane_nonlinear":
+        # the reference ships a distributions() dump of this aeroplane (test/input_for_testing.txt): keep its
+        # circulation, lift-coefficient and angle-of-attack columns as an independent golden vector
+        d = np.genfromtxt(os.path.join(REF, "test/input_for_testing.txt"), skip_header=1, dtype=None, encoding="utf-8")
+        gold["circ_file"] = np.array([row[31] for row in d], dtype=float)
+        gold["cl_file"] = np.array([row[21] for row in d], dtype=float)
+        gold["alpha_file"] = np.array([row[13] for row in d], dtype=float)
     if lean:
         for k in ("V_colsum", "dM_inv", "dM_visc", "dF_visc", "u_trailing_0", "u_trailing_1"):
             gold.pop(k)
@@ -187,7 +194,12 @@ def generate(name, inp, check=True, lean=False):
         gold["V_rows"] = V_rows[:3]
     meta = {"input": inp, "solver": sp, "FM": FM, "iterations": len(hist),
             "segment_names": [list(x) for x in tables["segment_names"]],
-            "reference": "usuaero/MachUpX v2.7.2 + oracle/ref_stubs", "n": n}
+            "reference": "usuaero/MachUpX v2.7.2 + oracle/ref_stubs", "n": n,
+            "aircraft": [{"name": ap.name, "q": list(map(float, ap.q)), "v": list(map(float, ap.v)),
+                          "p_bar": list(map(float, ap.p_bar)), "S_w": float(ap.S_w), "l_ref_lat": float(ap.l_ref_lat),
+                          "l_ref_lon": float(ap.l_ref_lon), "wind": list(map(float, scene._get_wind(ap.p_bar))),
+                          "rho": float(scene._get_density(ap.p_bar)), "segments": [sg.name for sg in ap.segments]}
+                         for ap in scene._airplane_objects]}
 
     if check and not lean:
         T = O.Tables(tables, ac_state)

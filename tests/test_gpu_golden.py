@@ -102,3 +102,22 @@ def test_lu_against_lapack():
     x, _ = dev.lu_solve_dense(A, b)
     xr = np.linalg.solve(A, b)
     assert np.abs(x - xr).max() / np.abs(xr).max() < 1e-12
+
+
+def test_c2_traditional_4000_control_points():
+    """BASELINE.json configs[1] at full size: circulation, CL/CD/Cm and the Newton count against the reference run."""
+    from machupx_b200.forces import AircraftFrame, assemble_fm
+    tables, g, meta, res = _run("c2_traditional_n4000")
+    assert tables["n"] == 4000
+    assert np.abs(res["gamma"] - g["gamma"]).max() / np.abs(g["gamma"]).max() < RTOL
+    assert np.abs(res["gamma_linear"] - g["gamma_linear"]).max() / np.abs(g["gamma_linear"]).max() < RTOL
+    assert res["iterations"] == meta["iterations"] == 11
+    frames = [AircraftFrame(a["name"], a["q"], a["v"], a["wind"], a["rho"], a["S_w"], a["l_ref_lat"], a["l_ref_lon"], a["segments"])
+              for a in meta["aircraft"]]
+    FM = assemble_fm(res["seg_fm"], frames)
+    name = meta["aircraft"][0]["name"]
+    ref_total = meta["FM"][name]["total"]
+    for key in ("CL", "CD", "Cm", "Cx", "Cz", "FL", "FD", "My"):
+        assert abs(FM[name]["total"][key] - ref_total[key]) <= RTOL * abs(ref_total[key]), key
+    # the numbers SURVEY.md section 6 recorded for this configuration
+    assert abs(ref_total["CL"] - 0.36518657437915686) < 1e-12 and abs(ref_total["CD"] - 0.014902688270872865) < 1e-12
