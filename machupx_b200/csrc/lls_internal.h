@@ -68,7 +68,9 @@ struct Scene {
     double* M = nullptr;
     // carved from the caller's work buffer
     double* W = nullptr;        // W_NF * ld
-    double* inv = nullptr;      // (ld / LU_NB) * 2 * LU_NB * LU_NB   inverse diagonal blocks (L then U)
+    double* inv = nullptr;      // 2 * LU_NB * LU_NB: factored diagonal block published by the LU's diag CTA (double-buffered)
+    int* lu_flags = nullptr;    // ld / LU_NB ints: flag[k] == lu_epoch once diagonal block k of the current factorisation is published
+    int lu_epoch = 0;           // factorisation counter (host)
     double* partial = nullptr;  // reduction scratch (>= 4096 doubles)
     double* scalars = nullptr;  // [0] ||R||^2  [1] min |pivot| ...   (device)
     int* status = nullptr;      // device status word

@@ -104,6 +104,29 @@ def test_lu_against_lapack():
     assert np.abs(x - xr).max() / np.abs(xr).max() < 1e-12
 
 
+@pytest.mark.parametrize("n", [64, 65, 130, 1000, 2047])
+def test_lu_sizes(n):
+    """Device LU (one fused launch per block step, look-ahead panel) at block-count edge cases: a single block,
+    one block plus one row, ragged padding, and sizes where most CTAs are plain trailing-update tiles."""
+    from machupx_b200 import layout as L
+    from machupx_b200.device import DeviceScene
+    ld = L.padded_ld(n)
+    tables = {"n": n, "ld": ld, "n_aircraft": 1, "n_segments": 1, "flags": L.FLAG_DEFAULT, "tab": np.zeros((L.NF, ld)),
+              "itab": np.zeros((L.NI, ld), dtype=np.int32), "airfoils": np.zeros((1, L.AF_STRIDE))}
+    dev = DeviceScene(tables)
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(n, n)) * (1.0 / np.sqrt(n)) + np.diag(3.0 + rng.random(n))
+    b = rng.normal(size=n)
+    xr = np.linalg.solve(A, b)
+    for rep in range(2):   # twice: the publish flags must work across factorisations (epoch)
+        x, LU = dev.lu_solve_dense(A, b)
+        assert np.abs(x - xr).max() / np.abs(xr).max() < 1e-12
+    # the factors themselves: L U == A
+    Lf = np.tril(LU[:n, :n], -1) + np.eye(n)
+    Uf = np.triu(LU[:n, :n])
+    assert np.abs(Lf @ Uf - A).max() / np.abs(A).max() < 1e-13
+
+
 def test_c2_traditional_4000_control_points():
     """BASELINE.json configs[1] at full size: circulation, CL/CD/Cm and the Newton count against the reference run."""
     from machupx_b200.forces import AircraftFrame, assemble_fm
