@@ -161,6 +161,7 @@ class Airplane:
 
     def set_control_state(self, control_state={}):
         """Deflections not given revert to zero (airplane.py:925-944)."""
+        self._controls_rev = getattr(self, "_controls_rev", 0) + 1   # lets Scene know the flap rows on the device are stale
         for key in self.current_control_state:
             self.current_control_state[key] = control_state.get(key, 0.0)
         for segment in self.wing_segments.values():

@@ -16,8 +16,9 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static size_t work_bytes_for(int ld) {
     size_t b = 0;
     b += align_up((size_t)W_NF * ld * 8, 256);
-    b += align_up((size_t)2 * LU_NB * LU_NB * 8, 256);      // published diagonal LU block (x2)
-    b += align_up((size_t)(ld / LU_NB + 1) * 4, 256);       // LU flags
+    b += align_up((size_t)LU_PUB_BYTES, 256);               // published diagonal LU block images (x2)
+    b += align_up((size_t)ld * LU_NB * 8, 256);             // inverse diagonal U blocks
+    b += align_up((size_t)2 * (ld / LU_NB + 1) * 4, 256);   // LU flags (factorisation, back-substitution)
     b += align_up((size_t)ld * 8, 256);  // partial
     b += 256;                            // scalars
     b += 256;                            // status
@@ -119,16 +120,18 @@ extern "C" int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab
     h->W = (double*)p;
     p += align_up((size_t)W_NF * h->ld * 8, 256);
     h->inv = (double*)p;
-    p += align_up((size_t)2 * LU_NB * LU_NB * 8, 256);
+    p += align_up((size_t)LU_PUB_BYTES, 256);
+    h->uinv = (double*)p;
+    p += align_up((size_t)h->ld * LU_NB * 8, 256);
     h->lu_flags = (int*)p;
-    p += align_up((size_t)(h->ld / LU_NB + 1) * 4, 256);
+    p += align_up((size_t)2 * (h->ld / LU_NB + 1) * 4, 256);
     h->partial = (double*)p;
     p += align_up((size_t)h->ld * 8, 256);
     h->scalars = (double*)p;
     p += 256;
     h->status = (int*)p;
     // the LU's publish flags compare against a per-handle epoch that starts at 0: clear them once here
-    LLS_CUDA_TRY(cudaMemset(h->lu_flags, 0, (size_t)(h->ld / LU_NB + 1) * 4));
+    LLS_CUDA_TRY(cudaMemset(h->lu_flags, 0, (size_t)2 * (h->ld / LU_NB + 1) * 4));
     h->lu_epoch = 0;
     return LLS_OK;
 }

@@ -36,6 +36,7 @@ inline void count_launch(int k = 1) { g_launches += (unsigned long long)k; }
 
 constexpr int LD_ALIGN = 64;   // leading dimension granularity (elements); equals the LU block size
 constexpr int LU_NB = 64;      // LU block size
+constexpr size_t LU_PUB_BYTES = 2 * (size_t)(2 * LU_NB * (LU_NB + 4) + LU_NB) * 8;   // two parities of the published diagonal-block image (lu.cu)
 
 // Per-control-point scratch ("row state"), field-major with the scene's ld.  Produced by the
 // flow-state and residual kernels, consumed by the assembly kernels.
@@ -68,8 +69,9 @@ struct Scene {
     double* M = nullptr;
     // carved from the caller's work buffer
     double* W = nullptr;        // W_NF * ld
-    double* inv = nullptr;      // 2 * LU_NB * LU_NB: factored diagonal block published by the LU's diag CTA (double-buffered)
-    int* lu_flags = nullptr;    // ld / LU_NB ints: flag[k] == lu_epoch once diagonal block k of the current factorisation is published
+    double* inv = nullptr;      // LU_PUB_BYTES: factored diagonal block images published by the LU's diag CTA (double-buffered)
+    double* uinv = nullptr;     // ld * LU_NB: inverse of every diagonal U block, left by the factorisation for the back-substitution chain
+    int* lu_flags = nullptr;    // 2 * (ld / LU_NB + 1) ints: [k] == lu_epoch once diagonal block k is published; [nblk + 1 + k] once x_k is
     int lu_epoch = 0;           // factorisation counter (host)
     double* partial = nullptr;  // reduction scratch (>= 4096 doubles)
     double* scalars = nullptr;  // [0] ||R||^2  [1] min |pivot| ...   (device)

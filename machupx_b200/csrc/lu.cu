@@ -24,10 +24,19 @@
 
 namespace lls {
 
+#ifdef LLS_LU_CLOCKS
+__device__ long long g_lu_clocks[16];
+#define LU_CLK(slot) do { if (role == DIAG && threadIdx.x == 0) g_lu_clocks[slot] = clock64(); } while (0)
+#else
+#define LU_CLK(slot) do { } while (0)
+#endif
+
 constexpr int NB = LU_NB;          // 64
 constexpr int TS = NB + 4;         // shared-memory row stride (doubles): conflict-free DMMA fragment loads
 constexpr int TILE_BYTES = NB * TS * 8;
 constexpr int LU_THREADS = 128;
+constexpr int PUB_DOUBLES = NB * TS + NB;       // published diagonal-block image: LU (padded rows, upper part scaled), 1/diag(U)
+static_assert((NB * TS / 2) % LU_THREADS == 0, "image copy assumes a whole number of double2 per thread");
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -43,18 +52,17 @@ __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
-// 64x64 tile global -> shared (row stride TS), optional scale; 128 threads
-__device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, size_t ldg, double scale) {
+// 64x64 tile global -> shared (row stride TS) with cp.async (16 bytes per request, all 16 requests of a thread in flight)
+__device__ __forceinline__ void load_tile_async(double* __restrict__ s, const double* __restrict__ g, size_t ldg) {
     const int t = threadIdx.x;
     const int c2 = t & 31, r0 = t >> 5;
-#pragma unroll 4
+#pragma unroll
     for (int r = r0; r < NB; r += 4) {
-        double2 v = *reinterpret_cast<const double2*>(g + (size_t)r * ldg + 2 * c2);
-        v.x *= scale;
-        v.y *= scale;
-        *reinterpret_cast<double2*>(s + r * TS + 2 * c2) = v;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s + r * TS + 2 * c2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(g + (size_t)r * ldg + 2 * c2) : "memory");
     }
 }
+__device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
 // shared (row stride TS) -> 64x64 tile in global memory, coalesced
 __device__ __forceinline__ void store_tile(double* __restrict__ g, size_t ldg, const double* __restrict__ s) {
@@ -85,6 +93,8 @@ __device__ __forceinline__ void mma_tile(const double* __restrict__ sA, const do
 }
 
 // accumulator fragments <-> a row-major tile (global with ldg, or shared with TS)
+// LOAD negates on the way in and the store negates on the way out: the tile product is accumulated as
+// -(C) + L U, so neither operand tile needs a sign flip in shared memory
 template <bool LOAD>
 __device__ __forceinline__ void acc_io(double (&acc)[4][4][2], double* __restrict__ g, size_t ldg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,94 +107,177 @@ __device__ __forceinline__ void acc_io(double (&acc)[4][4][2], double* __restric
             double2* p = reinterpret_cast<double2*>(g + (size_t)(wm + mi * 8 + gq) * ldg + wn + ni * 8 + 2 * q);
             if (LOAD) {
                 double2 v = *p;
-                acc[mi][ni][0] = v.x;
-                acc[mi][ni][1] = v.y;
+                acc[mi][ni][0] = -v.x;
+                acc[mi][ni][1] = -v.y;
             } else {
-                *p = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                *p = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
             }
         }
 }
 
 // ---- in-CTA factorisation of a 64 x 64 block held in shared memory (row stride TS) -------------------
 // 128 threads as a 16 x 8 grid; thread (ty, tx) keeps rows ty + 16 i (i < 4) and columns tx + 8 j (j < 8) in
-// registers (cyclic, so the shrinking active window stays balanced).  Per pivot p the owners publish row p and
-// column p through a double-buffered shared line, everyone rescales and applies the rank-1 update: one barrier
-// per pivot.  Returns min |pivot| and flags a zero / NaN pivot.
+// registers (cyclic, so the shrinking active window stays balanced).  Per pivot p the owners of row p and column p
+// publish them through a double-buffered shared line ALREADY MASKED (row entries left of / on the pivot and column
+// entries above / on it are zero), so the rank-1 update needs no compares: one barrier, a handful of 16-byte shared
+// loads, one reciprocal and (4 - I)(8 - J) DFMA per pivot.  The pivots are walked in 8 groups of 8 with the register
+// row I = p / 16 and column J = p / 8 that hold the pivot known at compile time, so no register array is ever indexed
+// dynamically and dead register rows / columns drop out of the update.  Multipliers (L) go straight to shared memory;
+// the registers end up holding U.
 struct PivotLine {
-    double row[2][NB];
-    double col[2][NB];
+    double row[2][NB];    // [buf][tx * 8 + j]   masked pivot row
+    double col[2][NB];    // [buf][ty * 4 + i]   masked pivot column (unscaled)
+    double rcp[NB];       // reciprocal pivots
+    double piv[2];
 };
 
-__device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine& pl, double& minpiv, bool& bad) {
+// 1 / d to ~1e-18 relative: hardware seed (reciprocal of the high word, ~2^-20) + one cubic Newton step.  Not
+// correctly rounded (neither needed nor expected of LU multipliers); 3 dependent DFMA instead of the 5 of `1.0 / d`.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+    const double e = fma(-d, x0, 1.0);
+    const double q = fma(e, e, e);
+    return fma(x0, q, x0);
+}
+
+template <int J>
+__device__ __forceinline__ void factor_group(double (&a)[4][8], PivotLine& pl, int ty, int tx) {
+    constexpr int I = J >> 1;
+    // compact rolled loop on purpose: these few hundred bytes of code run 8 times per group out of the instruction
+    // cache; the fully unrolled variant was fetch-bound and slower (measured on B200)
+#pragma unroll 1
+    for (int pp = 0; pp < 8; ++pp) {
+        const int p = 8 * J + pp, buf = pp & 1, pty = p & 15;
+        if (ty == pty) {            // part of row p lives in register row I
+            if (tx == pp) pl.piv[buf] = a[I][J];
+            double2* dst = reinterpret_cast<double2*>(&pl.row[buf][tx * 8]);
+            const double vJ = (tx > pp) ? a[I][J] : 0.0;
+            if (J & 1) {
+                dst[J / 2] = make_double2(0.0, vJ);
+            } else {
+                dst[J / 2] = make_double2(vJ, a[I][(J + 1) & 7]);
+            }
+#pragma unroll
+            for (int m = J / 2 + 1; m < 4; ++m) dst[m] = make_double2(a[I][2 * m], a[I][2 * m + 1]);
+        }
+        if (tx == pp) {             // part of column p lives in register column J
+            double2* dst = reinterpret_cast<double2*>(&pl.col[buf][ty * 4]);
+            const double vI = (ty > pty) ? a[I][J] : 0.0;
+            if (I & 1) {
+                dst[I / 2] = make_double2(0.0, vI);
+            } else {
+                dst[I / 2] = make_double2(vI, a[(I + 1) & 3][J]);
+            }
+            if (I / 2 == 0) dst[1] = make_double2(a[2][J], a[3][J]);
+        }
+        __syncthreads();
+        double r8[8], c4[4];
+        {
+            const double2* rr = reinterpret_cast<const double2*>(&pl.row[buf][tx * 8]);
+            const double2* cc = reinterpret_cast<const double2*>(&pl.col[buf][ty * 4]);
+            const double piv = pl.piv[buf];
+#pragma unroll
+            for (int m = J / 2; m < 4; ++m) {
+                const double2 v = rr[m];
+                r8[2 * m] = v.x;
+                r8[2 * m + 1] = v.y;
+            }
+            double2 cv[2];
+#pragma unroll
+            for (int m = I / 2; m < 2; ++m) cv[m] = cc[m];
+            const double rp = fast_rcp(piv);
+            if (ty == pty && tx == pp) pl.rcp[p] = rp;
+#pragma unroll
+            for (int m = I / 2; m < 2; ++m) {
+                c4[2 * m] = cv[m].x * rp;
+                c4[2 * m + 1] = cv[m].y * rp;
+            }
+        }
+        // column J of lanes tx == pp keeps the UNSCALED multipliers (their pivot-row entry is masked to zero), rows <= p
+        // keep U: both are finished off after the last pivot
+#pragma unroll
+        for (int i = I; i < 4; ++i)
+#pragma unroll
+            for (int j = J; j < 8; ++j) a[i][j] = fma(-c4[i], r8[j], a[i][j]);
+    }
+}
+
+__device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine& pl) {
     const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
     double a[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * TS + tx + 8 * j];
-    minpiv = 1e300;
-    bad = false;
-#pragma unroll 1
-    for (int p = 0; p < NB; ++p) {
-        const int buf = p & 1;
-        const int pi = p >> 4, pty = p & 15, pj = p >> 3, ptx = p & 7;
-        if (ty == pty) {
+    factor_group<0>(a, pl, ty, tx);
+    factor_group<1>(a, pl, ty, tx);
+    factor_group<2>(a, pl, ty, tx);
+    factor_group<3>(a, pl, ty, tx);
+    factor_group<4>(a, pl, ty, tx);
+    factor_group<5>(a, pl, ty, tx);
+    factor_group<6>(a, pl, ty, tx);
+    factor_group<7>(a, pl, ty, tx);
+    __syncthreads();      // pl.rcp complete
+    // registers hold U on and above the diagonal and the unscaled multipliers below it: L(r, c) = a(r, c) / U(c, c)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (i == pi) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) pl.row[buf][tx + 8 * j] = a[i][j];
-                }
-        }
-        if (tx == ptx) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j == pj) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) pl.col[buf][ty + 16 * i] = a[i][j];
-                }
-        }
-        __syncthreads();
-        const double piv = pl.row[buf][p];
-        minpiv = fmin(minpiv, fabs(piv));
-        bad |= !(fabs(piv) > 0.0);
-        const double rp = 1.0 / piv;
-        double r8[8], c4[4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r8[j] = pl.row[buf][tx + 8 * j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c4[i] = pl.col[buf][ty + 16 * i] * rp;
+    for (int j = 0; j < 8; ++j) {
+        const double rc = pl.rcp[tx + 8 * j];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int row = ty + 16 * i;
-            if (row > p) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = tx + 8 * j;
-                    if (col > p) a[i][j] = fma(-c4[i], r8[j], a[i][j]);
-                    else if (col == p) a[i][j] = c4[i];
-                }
-            }
+            const int row = ty + 16 * i, col = tx + 8 * j;
+            sC[row * TS + col] = (row > col) ? a[i][j] * rc : a[i][j];
         }
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * TS + tx + 8 * j] = a[i][j];
     __syncthreads();
 }
 
-// forward substitution  T x = c  with a lower-triangular T held column-major in shared memory
-// (T(r, q) at sT[q * TS + r]) and its reciprocal diagonal dinv; x lives in registers (one system per thread).
-__device__ __forceinline__ void trsv_lower64(const double* __restrict__ sT, const double* __restrict__ dinv, double (&x)[NB]) {
+// ---- X W = C for an upper-triangular W, in place on a 64 x 64 tile held in the same 2-D cyclic register layout -----
+// W is given PRE-SCALED by its reciprocal diagonal, W'(p, c) = W(p, c) / W(p, p) for c > p, at sW[p * wr + c * wc],
+// and dinv = 1 / diag W.  With a_p the current (unscaled) pivot column of the tile, x_p = a_p dinv_p and
+// a_c -= a_p W'(p, c): the only dependent work between two pivots is one shuffle and one DFMA.  Column p of the tile
+// lives in the 8 lanes that share ty, so the multipliers travel by warp shuffle: no barrier in the whole solve.  Serves
+//   L21 = C U11^-1              (sW = published image, upper part = U11 rows scaled; wr = TS, wc = 1)
+//   U12^T = C^T (L11^T)^-1      (W = L11^T, unit diagonal: W(p, c) = L11(c, p) = image[c][p]; wr = 1, wc = TS; dinv = 1;
+//                                the tile is loaded / stored transposed)
+//   inv(U11) = I U11^-1         (tile = identity), used by the back-substitution chain.
+template <int J, bool TR>
+__device__ __forceinline__ void panel_group(double (&a)[4][8], const double* __restrict__ sW, const double* __restrict__ dinv,
+                                            int tx, int lane) {
+    constexpr int wr = TR ? 1 : TS, wc = TR ? TS : 1;
+#pragma unroll 1
+    for (int pp = 0; pp < 8; ++pp) {
+        const int p = 8 * J + pp;
+        const int src = (lane & ~7) | pp;
+        const double* wrow = sW + p * wr + tx * wc;
+        double w[8];
+        w[J] = (tx > pp) ? wrow[8 * J * wc] : 0.0;
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-        x[q] *= dinv[q];
-        const double xq = x[q];
+        for (int j = J + 1; j < 8; ++j) w[j] = wrow[8 * j * wc];
+        const double rp = TR ? 1.0 : dinv[p];
+        double ap[4];
 #pragma unroll
-        for (int r = q + 1; r < NB; ++r) x[r] = fma(-sT[q * TS + r], xq, x[r]);
+        for (int i = 0; i < 4; ++i) ap[i] = __shfl_sync(0xffffffffu, a[i][J], src);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i][J] = (tx == pp) ? ap[i] * rp : fma(-ap[i], w[J], a[i][J]);
+#pragma unroll
+        for (int j = J + 1; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i][j] = fma(-ap[i], w[j], a[i][j]);
     }
+}
+
+template <bool TR>
+__device__ __forceinline__ void panel_solve(double (&a)[4][8], const double* __restrict__ sW, const double* __restrict__ dinv) {
+    const int tx = threadIdx.x & 7, lane = threadIdx.x & 31;
+    panel_group<0, TR>(a, sW, dinv, tx, lane);
+    panel_group<1, TR>(a, sW, dinv, tx, lane);
+    panel_group<2, TR>(a, sW, dinv, tx, lane);
+    panel_group<3, TR>(a, sW, dinv, tx, lane);
+    panel_group<4, TR>(a, sW, dinv, tx, lane);
+    panel_group<5, TR>(a, sW, dinv, tx, lane);
+    panel_group<6, TR>(a, sW, dinv, tx, lane);
+    panel_group<7, TR>(a, sW, dinv, tx, lane);
 }
 
 // y = L^-1 b for the unit-lower factor held row-major in sC; warp 0 only, lane l keeps b[l] and b[l + 32]
@@ -208,13 +301,13 @@ __device__ __forceinline__ void forward_rhs_warp(const double* __restrict__ sC, 
 template <bool FIRST>
 __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restrict__ M, int ld, int k, int rem,
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
-                                                                int* __restrict__ flags, int epoch,
+                                                                double* __restrict__ uinv, int* __restrict__ flags, int epoch,
                                                                 double* __restrict__ scalars, int* __restrict__ status) {
     extern __shared__ __align__(16) double sm[];
     double* sA = sm;
     double* sB = sm + NB * TS;
-    __shared__ PivotLine pl;
-    __shared__ double dinv[NB];
+    __shared__ __align__(16) PivotLine pl;
+    __shared__ __align__(16) double dinv[NB];
     const int t = threadIdx.x;
     const int b = blockIdx.x;
     const int base = FIRST ? 0 : k + 1;  // first block row/col of the trailing matrix
@@ -233,116 +326,202 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
         bj = base + 1 + o % (rem - 1);
     }
     double* gC = M + (size_t)bi * NB * ld + (size_t)bj * NB;
-    double acc[4][4][2];
+    LU_CLK(0);
     if (!FIRST) {
-        load_tile(sA, M + (size_t)bi * NB * ld + (size_t)k * NB, ld, -1.0);   // -L[bi,k]
-        load_tile(sB, M + (size_t)k * NB * ld + (size_t)bj * NB, ld, 1.0);    //  U[k,bj]
-        acc_io<true>(acc, gC, ld);
+        double acc[4][4][2];
+        load_tile_async(sA, M + (size_t)bi * NB * ld + (size_t)k * NB, ld);   // L[bi,k]
+        load_tile_async(sB, M + (size_t)k * NB * ld + (size_t)bj * NB, ld);   // U[k,bj]
+        acc_io<true>(acc, gC, ld);                                            // -C
+        async_wait_all();
         __syncthreads();
-        mma_tile(sA, sB, acc);
+        LU_CLK(1);
+        mma_tile(sA, sB, acc);                                                // -C + L U
+        LU_CLK(2);
         if (role == OTHER) {
-            acc_io<false>(acc, gC, ld);
+            acc_io<false>(acc, gC, ld);                                       // C - L U
             return;
         }
-        if (rhs != nullptr && bj == base && t < NB) {   // b[bi] -= L[bi,k] y_k   (sA holds -L)
+        if (rhs != nullptr && bj == base && t < NB) {   // b[bi] -= L[bi,k] y_k
             double s = 0.0;
             const double* yk = rhs + (size_t)k * NB;
 #pragma unroll 8
             for (int q = 0; q < NB; ++q) s = fma(sA[t * TS + q], yk[q], s);
-            rhs[(size_t)bi * NB + t] += s;
+            rhs[(size_t)bi * NB + t] -= s;
         }
         __syncthreads();
-        acc_io<false>(acc, sB, TS);   // C, row-major in shared memory
+        acc_io<false>(acc, sB, TS);   // C - L U, row-major in shared memory
         __syncthreads();
     } else {
-        load_tile(sB, gC, ld, 1.0);
+        load_tile_async(sB, gC, ld);
+        async_wait_all();
         __syncthreads();
     }
     double* sC = sB;
     const int blk = base;                       // index of the diagonal block being factored
-    double* dl = dbuf + (size_t)(blk & 1) * NB * NB;
+    // published image of the factored diagonal block (per parity), already in the padded shared-memory layout so that
+    // consumers copy it flat: row-major LU with the strictly upper part scaled by 1 / diag(U), then 1 / diag(U)
+    double* img = dbuf + (size_t)(blk & 1) * PUB_DOUBLES;
+    constexpr int IMG2 = NB * TS / 2;           // double2 elements of the image
 
     if (role == DIAG) {
-        double minpiv;
-        bool bad;
-        factor_block(sC, pl, minpiv, bad);
-        store_tile(dl, NB, sC);
+        LU_CLK(3);
+        factor_block(sC, pl);
+        LU_CLK(4);
+        if (t < NB) dinv[t] = 1.0 / sC[t * TS + t];
+        __syncthreads();
+        for (int e = t; e < NB * NB; e += LU_THREADS) {
+            const int r = e >> 6, c = e & 63;
+            const double v = sC[r * TS + c];
+            sA[r * TS + c] = (c > r) ? v * dinv[r] : v;
+        }
+        __syncthreads();
+        {
+            double2* g0 = reinterpret_cast<double2*>(img);
+            const double2* s0 = reinterpret_cast<const double2*>(sA);
+#pragma unroll
+            for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
+            if (t < NB) img[NB * TS + t] = dinv[t];
+        }
         __threadfence();
         __syncthreads();
         if (t == 0) st_release(flags + blk, epoch);
+        LU_CLK(5);
+        // everything below is off the critical path of the panel CTAs
         store_tile(gC, ld, sC);
+        if (t < NB) {       // smallest pivot magnitude and zero / NaN pivots (growth guard of the unpivoted factorisation)
+            const double d = fabs(sC[t * TS + t]);
+            double m = d;
+            bool bad = !(d > 0.0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            bad = __any_sync(0xffffffffu, bad);
+            if ((t & 31) == 0) {
+                if (bad) atomicOr(status, LLS_STATUS_NAN);
+                pl.piv[t >> 5] = m;
+            }
+        }
+        __syncthreads();
         if (t == 0) {
-            if (bad) atomicOr(status, LLS_STATUS_NAN);
-            scalars[1] = (blk == 0) ? minpiv : fmin(minpiv, scalars[1]);
+            const double m = fmin(pl.piv[0], pl.piv[1]);
+            scalars[1] = (blk == 0) ? m : fmin(m, scalars[1]);
         }
         if (rhs != nullptr && t < 32) forward_rhs_warp(sC, rhs + (size_t)blk * NB);
-        return;
-    }
-
-    // panel roles: wait for the factored diagonal block
-    if (t == 0) {
-        while (ld_acquire(flags + blk) != epoch) __nanosleep(64);
-    }
-    __syncthreads();
-    {
-        // sT(r, q) at sA[q * TS + r]:  UROW needs T = L11 (unit lower), LCOL needs T = U11^T
-        const int c = t & 63, r0 = t >> 6;
-        for (int r = r0; r < NB; r += 2) {
-            const double v = __ldcg(dl + r * NB + c);
-            if (role == UROW) sA[c * TS + r] = v;   // T(r, c) = L(r, c), stored at [q = c][r]
-            else sA[r * TS + c] = v;                // T(c, r) = U(r, c), stored at [q = r][c]
+        // W = U11, pre-scaled rows in sA: the solve below turns the identity into inv(U11)
+    } else {
+        // panel roles: wait for the factored diagonal block
+        if (t == 0) {
+            while (ld_acquire(flags + blk) != epoch) __nanosleep(32);
         }
-        if (t < NB) dinv[t] = (role == UROW) ? 1.0 : 1.0 / __ldcg(dl + t * NB + t);
+        __syncthreads();
+        const double2* g = reinterpret_cast<const double2*>(img);
+        double2* sT2 = reinterpret_cast<double2*>(sA);
+        double2 v[IMG2 / LU_THREADS];
+#pragma unroll
+        for (int u = 0; u < IMG2 / LU_THREADS; ++u) v[u] = __ldcg(g + t + u * LU_THREADS);
+#pragma unroll
+        for (int u = 0; u < IMG2 / LU_THREADS; ++u) sT2[t + u * LU_THREADS] = v[u];
+        if (t < NB) dinv[t] = (role == UROW) ? 1.0 : __ldcg(img + NB * TS + t);
+        // LCOL: W = U11 (scaled upper part, row-major); UROW (transposed problem): W = L11^T, W(p, c) = image[c][p]
+        __syncthreads();
+    }
+    {
+        // 2-D cyclic register tile: a[i][j] <-> (row ty + 16 i, col tx + 8 j) of X; UROW works on the transposed tile
+        const int ty = t >> 3, tx = t & 7;
+        const int sr = (role == UROW) ? 1 : TS, sc = (role == UROW) ? TS : 1;
+        double a[4][8];
+        if (role == DIAG) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = (ty + 16 * i == tx + 8 * j) ? 1.0 : 0.0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc];
+        }
+        LU_CLK(6);
+        if (role == UROW) panel_solve<true>(a, sA, dinv);
+        else panel_solve<false>(a, sA, dinv);
+        LU_CLK(7);
+        __syncthreads();   // everyone is done reading the tile (and, in the diag CTA, the factors for the right-hand side)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
     }
     __syncthreads();
-    if (t < NB) {
-        const int se = (role == UROW) ? TS : 1, st = (role == UROW) ? 1 : TS;   // x[e] = C(e, t) or C(t, e)
-        double x[NB];
-#pragma unroll
-        for (int e = 0; e < NB; ++e) x[e] = sC[e * se + t * st];
-        trsv_lower64(sA, dinv, x);
-#pragma unroll
-        for (int e = 0; e < NB; ++e) sC[e * se + t * st] = x[e];
-    }
-    __syncthreads();
-    store_tile(gC, ld, sC);
+    if (role == DIAG) store_tile(uinv + (size_t)blk * NB * NB, NB, sC);
+    else store_tile(gC, ld, sC);
+    LU_CLK(8);
 }
 
-// ---- block back-substitution, one launch per block column k (from the last to the first) -------------
-// every CTA i <= k solves U_kk x_k = y_k (warp-serial, 64 steps); CTA k stores x_k, CTAs i < k fold it into y_i
-__global__ void __launch_bounds__(NB) lu_backsolve_kernel(const double* __restrict__ M, int ld, int k,
-                                                          double* __restrict__ rhs, double* __restrict__ x) {
-    __shared__ double xk[NB];
-    __shared__ double sU[NB][NB + 1];
-    const int t = threadIdx.x, i = blockIdx.x;
-    const double* Ukk = M + (size_t)k * NB * ld + (size_t)k * NB;
-    for (int r = 0; r < NB; ++r) sU[r][t] = Ukk[(size_t)r * ld + t];
-    xk[t] = rhs[(size_t)k * NB + t];
-    __syncthreads();
-    if (t < 32) {
-        double x0 = xk[t], x1 = xk[t + 32];
-#pragma unroll 1
-        for (int q = NB - 1; q >= 0; --q) {
-            const double d = 1.0 / sU[q][q];
-            double xq = __shfl_sync(0xffffffffu, (q < 32) ? x0 : x1, q & 31) * d;
-            if (t == (q & 31)) {
-                if (q < 32) x0 = xq; else x1 = xq;
-            }
-            if (t < q) x0 = fma(-sU[t][q], xq, x0);
-            if (t + 32 < q) x1 = fma(-sU[t + 32][q], xq, x1);
+// ---- block back-substitution as ONE launch: a chain of CTAs, one per block row --------------------------------
+// CTA of block row i folds x_k (k = last .. i+1) into y_i as they are published, then x_i = inv(U_ii) y_i with the
+// inverse diagonal block the factorisation left in uinv, and publishes x_i.  Blocks are numbered from the LAST block
+// row, so every producer is scheduled before its consumers.  Thread t owns row t of the tile; the tile row and the
+// inverse row are fetched into registers before the wait, so the chain step is: flag -> 64-double x_k -> two
+// 64-term dot products -> release.
+constexpr int BS_THREADS = NB;
+
+__global__ void __launch_bounds__(BS_THREADS) lu_backsolve_chain_kernel(const double* __restrict__ M, int ld, int nblk,
+                                                                        const double* __restrict__ uinv,
+                                                                        const double* __restrict__ y, double* __restrict__ x,
+                                                                        int* __restrict__ xflags, int epoch) {
+    __shared__ __align__(16) double sx[NB];
+    const int t = threadIdx.x;
+    const int bi = nblk - 1 - blockIdx.x;
+    double yt = y[(size_t)bi * NB + t];
+    double2 ui[NB / 2];
+    {
+        const double2* g = reinterpret_cast<const double2*>(uinv + (size_t)bi * NB * NB + (size_t)t * NB);
+#pragma unroll
+        for (int c = 0; c < NB / 2; ++c) ui[c] = g[c];
+    }
+    for (int k = nblk - 1; k > bi; --k) {
+        double2 u[NB / 2];
+        {
+            const double2* g = reinterpret_cast<const double2*>(M + ((size_t)bi * NB + t) * ld + (size_t)k * NB);
+#pragma unroll
+            for (int c = 0; c < NB / 2; ++c) u[c] = g[c];
         }
-        xk[t] = x0;
-        xk[t + 32] = x1;
+        if (t == 0) {
+            while (ld_acquire(xflags + k) != epoch) __nanosleep(20);
+        }
+        __syncthreads();
+        sx[t] = __ldcg(x + (size_t)k * NB + t);
+        __syncthreads();
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const double2* sx2 = reinterpret_cast<const double2*>(sx);
+#pragma unroll
+        for (int c = 0; c < NB / 2; c += 2) {
+            const double2 a = sx2[c], b = sx2[c + 1];
+            s0 = fma(u[c].x, a.x, s0);
+            s1 = fma(u[c].y, a.y, s1);
+            s2 = fma(u[c + 1].x, b.x, s2);
+            s3 = fma(u[c + 1].y, b.y, s3);
+        }
+        yt -= (s0 + s1) + (s2 + s3);
+        __syncthreads();
     }
+    sx[t] = yt;
     __syncthreads();
-    if (i == k) {
-        x[(size_t)k * NB + t] = xk[t];
-    } else {
-        const double* U = M + (size_t)i * NB * ld + (size_t)k * NB;
-        double a = 0.0;
-        for (int q = 0; q < NB; ++q) a += U[(size_t)t * ld + q] * xk[q];
-        rhs[(size_t)i * NB + t] -= a;
+    {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const double2* sx2 = reinterpret_cast<const double2*>(sx);
+#pragma unroll
+        for (int c = 0; c < NB / 2; c += 2) {
+            const double2 a = sx2[c], b = sx2[c + 1];
+            s0 = fma(ui[c].x, a.x, s0);
+            s1 = fma(ui[c].y, a.y, s1);
+            s2 = fma(ui[c + 1].x, b.x, s2);
+            s3 = fma(ui[c + 1].y, b.y, s3);
+        }
+        x[(size_t)bi * NB + t] = (s0 + s1) + (s2 + s3);
     }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) st_release(xflags + bi, epoch);
 }
 
 // forward substitution for lls_lu_solve: every CTA i >= k solves L_kk y_k = b_k; CTA k stores it, the others fold it in
@@ -377,6 +556,12 @@ __global__ void __launch_bounds__(NB) lu_forwardsolve_kernel(const double* __res
     }
 }
 
+#ifdef LLS_LU_CLOCKS
+extern "C" int lls_debug_lu_clocks(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_lu_clocks, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 static bool g_attr_done = false;
 
 static int lu_prepare(Scene* s) {
@@ -396,10 +581,8 @@ int lu_solve_only(Scene* s, const double* M, double* rhs, cudaStream_t st) {
         lu_forwardsolve_kernel<<<nblk - k, NB, 0, st>>>(M, ld, k, rhs, y);
         count_launch();
     }
-    for (int k = nblk - 1; k >= 0; --k) {
-        lu_backsolve_kernel<<<k + 1, NB, 0, st>>>(M, ld, k, y, rhs);
-        count_launch();
-    }
+    lu_backsolve_chain_kernel<<<nblk, BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, y, rhs, s->lu_flags + nblk + 1, ++s->lu_epoch);
+    count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }
@@ -408,23 +591,21 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     const int ld = s->ld, nblk = ld / NB;
     LLS_TRY(lu_prepare(s));
     const int epoch = ++s->lu_epoch;
-    double* dbuf = s->inv;          // 2 x (NB x NB) published diagonal factors
+    double* dbuf = s->inv;          // 2 x PUB_DOUBLES published diagonal factors
     int* flags = s->lu_flags;
     {
         const int rem = nblk;       // block 0 and its panel
-        lu_step_kernel<true><<<2 * rem - 1, LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, -1, rem, rhs, dbuf, flags, epoch, s->scalars, s->status);
+        lu_step_kernel<true><<<2 * rem - 1, LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status);
         count_launch();
     }
     for (int k = 0; k + 1 < nblk; ++k) {
         const int rem = nblk - 1 - k;
-        lu_step_kernel<false><<<rem * rem, LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, flags, epoch, s->scalars, s->status);
+        lu_step_kernel<false><<<rem * rem, LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status);
         count_launch();
     }
     if (rhs) {
-        for (int k = nblk - 1; k >= 0; --k) {
-            lu_backsolve_kernel<<<k + 1, NB, 0, st>>>(M, ld, k, rhs, x);
-            count_launch();
-        }
+        lu_backsolve_chain_kernel<<<nblk, BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, rhs, x, s->lu_flags + nblk + 1, epoch);
+        count_launch();
     }
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;

@@ -77,6 +77,11 @@ class DeviceScene:
         self.d_itab.copy_(torch.from_numpy(itab))
         self.d_af.copy_(torch.from_numpy(af))
 
+    def upload_rows(self, tab, fields):
+        """Re-uploads single rows of the double table (control deflections change only the flap rows)."""
+        for f in fields:
+            self.d_tab[f].copy_(torch.from_numpy(np.ascontiguousarray(tab[f], dtype=np.float64)))
+
     def upload_state(self, ac_state):
         self.h_ac.copy_(torch.from_numpy(np.ascontiguousarray(ac_state, dtype=np.float64).reshape(self.n_aircraft, L.AC_STRIDE)))
         self.d_ac.copy_(self.h_ac, non_blocking=True)

@@ -41,6 +41,27 @@ def flap_terms(delta, c_f):
     return delta * eps, delta * dcm, 0.002 * np.abs(delta) * 180.0 / np.pi
 
 
+def flap_rows(scene):
+    """The table rows that change with the control state only: {field index: (n,) array} in scene order."""
+    airplanes = list(scene._airplane_objects)
+    n = int(sum(a.N for a in airplanes))
+    rows = {f: np.zeros(n) for f in (L.F_FLAP_DA, L.F_FLAP_DCM, L.F_FLAP_DCD, L.F_FLAP_DEFL, L.F_FLAP_CF)}
+    k = 0
+    for ap in airplanes:
+        for seg in ap.segments:
+            sl = slice(k, k + seg.N)
+            delta = np.asarray(seg._delta_flap, dtype=float)
+            c_f = np.asarray(seg._cp_c_f, dtype=float)
+            da, dcm, dcd = flap_terms(delta, c_f)
+            rows[L.F_FLAP_DA][sl] = da
+            rows[L.F_FLAP_DCM][sl] = dcm
+            rows[L.F_FLAP_DCD][sl] = dcd
+            rows[L.F_FLAP_DEFL][sl] = delta
+            rows[L.F_FLAP_CF][sl] = c_f
+            k += seg.N
+    return rows
+
+
 def solver_flags(scene):
     f = 0
     if scene._use_swept_sections:
