@@ -27,6 +27,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one lu_step_kernel launch (block step k = 8 of an N = 4000 factorisation,
+# 54 x 54 = 2916 tiles) from the `ncu --set full` capture summarised in profiles/r1_lu_step_full.txt.  Algorithmic bytes
+# of that launch: read + write of the trailing matrix, 2 x 8 x (54 x 64)^2 = 191 MB; the 126 MB L2 keeps part of it.
+NCU_LU_TRAFFIC = {"bytes_per_launch": 137.6e6, "algorithmic_bytes_per_launch": 191.1e6,
+                  "launch": "lu_step_kernel, block step 8 of 63 (2916 tiles) at N=4000", "source": "profiles/r1_lu_step_full.txt"}
 METRIC = "lifting-line solves/sec"
 UNIT = "solves/s"
 
@@ -200,13 +205,25 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    import copy
+    import warnings
+    from machupx_b200 import Scene
+    from machupx_b200.tables import build_aircraft_state
     tables, ac_state, g, meta = load_workload(args.workload)
     sp = meta["solver"]
     nonlinear = sp["type"] == "nonlinear"
-    if world > 1:   # alpha sweep sharded by case: rank r flies at alpha0 + 0.25 deg * r
-        ac_state = with_alpha(ac_state, 2.0 + 0.25 * rank, meta)
-    dev = DeviceScene(tables)
+    # the public API object: JSON input of the fixture -> Scene (host geometry, O(N) tables) -> DeviceScene
+    scene = Scene(copy.deepcopy(meta["input"]))
+    if world > 1:   # alpha sweep sharded by case: rank r flies at alpha0 + 0.25 deg * r (first aircraft)
+        name = list(scene._airplanes.keys())[0]
+        scene._airplanes[name].set_aerodynamic_state(alpha=2.0 + 0.25 * rank)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scene.solve_forces()
+    dev = scene._device
     lib = dev.lib
+    tables = scene._tables
+    ac_state = build_aircraft_state(scene)
 
     def solve_resident():
         dev.flow_state()
@@ -220,11 +237,11 @@ def run_ours(args):
         return it
 
     def solve_e2e():
-        dev.upload_state(ac_state)      # pinned host -> device, every step
-        solve_resident()
-        dev.h_seg_fm.copy_(dev.d_seg_fm, non_blocking=True)   # device -> host read of the force sums
-        torch.cuda.current_stream().synchronize()
-        return dev.h_seg_fm.numpy()
+        # the call a user makes: Scene.solve_forces() -> pinned host->device copy of the flight state, all kernels,
+        # device->host read of the residual norms and the per-segment force sums, FM dictionary on the host
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return scene.solve_forces()
 
     def barrier():
         if world > 1:
@@ -261,7 +278,7 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     h2d = (dev.bytes_h2d - h2d0) // args.steps
-    d2h = dev.h_seg_fm.numel() * 8 + 8 * (iters + 1 if nonlinear else 0)   # force sums + the residual norm read each Newton iteration
+    d2h = (dev.bytes_d2h - d2h0) // args.steps + (8 * (iters + 1) + 4 if nonlinear else 4)   # force sums + residual norm per Newton iteration + status word
 
     clocks = sampler.stop() if rank == 0 else None
 
@@ -346,9 +363,9 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "blocked FP64 LU factorisation (lu_diag/lu_panel/lu_update launches; trailing update on DMMA mma.sync m8n8k4)",
+        "roofline": {"kernel": "lu_step_kernel: blocked FP64 LU factorisation, one launch per 64-column block step (trailing update on DMMA mma.sync m8n8k4, next panel factored in the same launch) + lu_backsolve_chain_kernel",
                      "bound": "tensor", "achieved": lu_tflops, "peak": fp64_dmma, "unit": "TFLOP/s",
-                     "frac": lu_tflops / fp64_dmma if fp64_dmma else None, "traffic": None,
+                     "frac": lu_tflops / fp64_dmma if fp64_dmma else None, "traffic": NCU_LU_TRAFFIC,
                      "peak_source": "FP64 DMMA probe run live by this process (MEASURED_PEAKS.json has no FP64 entry)",
                      "flops_per_solve": lu_flops, "ms_per_solve": lu_ms, "factorisations_per_solve": n_fact},
         "kernels": kernels,
