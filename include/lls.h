@@ -167,6 +167,27 @@ int lls_destroy(lls_scene* h);
 int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab, const double* d_airfoils,
              double* d_out, double* d_vji, double* d_mat, void* d_work, size_t work_bytes);
 
+/* Batch of `ncases` independent flight states of ONE geometry (alpha / beta / rate sweeps, finite-difference stencils of
+ * the derivative and trim drivers: scene.py:1876-2437, 2440-2640).  The reference runs them as a serial Python loop of
+ * set_aircraft_state + solve_forces; here one set of launches solves all cases (case index = blockIdx.z).
+ * d_tab / d_itab / d_airfoils are shared; d_out, d_vji, d_mat and d_work hold ncases consecutive copies of the
+ * single-scene buffers (sizes from lls_query_sizes; work_bytes_per_case a multiple of 256, >= work_bytes).
+ * d_ctl: 2 * ncases + 4 int32 (active mask, Newton iteration counts, number of active cases).
+ * After this call lls_set_state expects ncases * n_aircraft * LLS_AC_STRIDE doubles, lls_flow_state,
+ * lls_build_influence, lls_solve_linear and lls_integrate (ncases * n_segments * 12 doubles) act on every case, and
+ * lls_solve_nonlinear_batch replaces lls_solve_nonlinear.  lls_bind returns the handle to a single scene. */
+int lls_bind_batch(lls_scene* h, int ncases, const double* d_tab, const int32_t* d_itab, const double* d_airfoils,
+                   double* d_out, double* d_vji, double* d_mat, void* d_work, size_t work_bytes_per_case, int32_t* d_ctl);
+
+/* Newton iteration of every case of the bound batch in lock step; a case leaves the iteration when its residual norm
+ * falls below `convergence` exactly as the reference's `while` test does (scene.py:853), so per-case iteration counts
+ * equal those of separate solves.  Host outputs, ncases entries each. */
+int lls_solve_nonlinear_batch(lls_scene* h, double convergence, double relaxation, int max_iterations, void* stream,
+                              int* iterations, double* final_error, int* status);
+
+/* Status bits of every case of the bound batch (host array, ncases entries). */
+int lls_get_status_batch(lls_scene* h, void* stream, int* status);
+
 /* Per-aircraft flight state, n_aircraft * LLS_AC_STRIDE doubles on the device
  * (reference: Airplane.set_state airplane.py:105-213 -> scene.py:562-582). */
 int lls_set_state(lls_scene* h, const double* d_ac_state);

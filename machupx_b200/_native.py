@@ -5,7 +5,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblls.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class LlsError(RuntimeError):
@@ -29,6 +29,9 @@ SIGNATURES = {
     "lls_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i]),
     "lls_destroy": (_i, [_vp]),
     "lls_bind": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t]),
+    "lls_bind_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "lls_solve_nonlinear_batch": (_i, [_vp, _d, _d, _i, _vp, _pi, _pd, _pi]),
+    "lls_get_status_batch": (_i, [_vp, _vp, _pi]),
     "lls_set_state": (_i, [_vp, _vp]),
     "lls_flow_state": (_i, [_vp, _vp]),
     "lls_build_influence": (_i, [_vp, _d, _vp]),

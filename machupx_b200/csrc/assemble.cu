@@ -13,7 +13,9 @@ namespace lls {
 // ---------------------------------------------------------------------------------------------
 // linear system rows: g_i = -(V_inf CLa dS)_i u_n_i, diag_i = 2 |v_inf_rot x dl|, b_i     (scene.py:811-824)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) linear_rows_kernel(int n, int ld, int flags, const double* __restrict__ tab, double* __restrict__ W) {
+__global__ void __launch_bounds__(128) linear_rows_kernel(int n, int ld, int flags, const double* __restrict__ tab, double* __restrict__ W,
+                                                          CaseStrides cs) {
+    W = case_work_ptr(W, cs.work);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double Vref = (flags & LLS_FLAG_IN_PLANE) ? W[(size_t)W_VINF_IP * ld + i] : W[(size_t)W_VINF_MAG * ld + i];
@@ -40,7 +42,11 @@ constexpr int ASM_ROWS = 16;
 template <bool NEWTON>
 __global__ void __launch_bounds__(256) assemble_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                        const double* __restrict__ W, const double* __restrict__ V,
-                                                       double* __restrict__ M) {
+                                                       double* __restrict__ M, CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    W = case_work_ptr(W, cs.work);
+    V = case_ptr(V, cs.V);
+    M = case_ptr(M, cs.M);
     __shared__ double sg[3][ASM_ROWS], sws[3][ASM_ROWS], se[3][ASM_ROWS], sdiag[ASM_ROWS];
     const int row0 = blockIdx.y * ASM_ROWS;
     if (threadIdx.x < ASM_ROWS) {
@@ -104,7 +110,13 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                            const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                            const double* __restrict__ V, double* __restrict__ W,
-                                                           double* __restrict__ out, double* __restrict__ partial, int vel_only) {
+                                                           double* __restrict__ out, double* __restrict__ partial, int vel_only,
+                                                           CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    V = case_ptr(V, cs.V);
+    W = case_work_ptr(W, cs.work);
+    out = case_ptr(out, cs.out);
+    partial = case_work_ptr(partial, cs.work);
     const int i = blockIdx.x;
     const double* gamma = out + (size_t)LLS_O_GAMMA * ld;
     const double2* v0 = reinterpret_cast<const double2*>(V + (size_t)i * 3 * ld);
@@ -193,7 +205,11 @@ __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int fl
 }
 
 // deterministic sum of partial[0..n) -> scalars[slot]
-__global__ void __launch_bounds__(256) sum_kernel(int n, const double* __restrict__ partial, double* __restrict__ scalars, int slot) {
+__global__ void __launch_bounds__(256) sum_kernel(int n, const double* __restrict__ partial, double* __restrict__ scalars, int slot,
+                                                  CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    partial = case_work_ptr(partial, cs.work);
+    scalars = case_work_ptr(scalars, cs.work);
     __shared__ double red[8];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
@@ -207,33 +223,40 @@ __global__ void __launch_bounds__(256) sum_kernel(int n, const double* __restric
     }
 }
 
-__global__ void __launch_bounds__(128) newton_update_kernel(int n, int ld, double relaxation, const double* __restrict__ W, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) newton_update_kernel(int n, int ld, double relaxation, const double* __restrict__ W, double* __restrict__ out,
+                                                            CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    W = case_work_ptr(W, cs.work);
+    out = case_ptr(out, cs.out);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[(size_t)LLS_O_GAMMA * ld + i] += relaxation * W[(size_t)W_X * ld + i];       // scene.py:899
 }
 
-__global__ void __launch_bounds__(128) copy_gamma_kernel(int n, int ld, const double* __restrict__ W, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) copy_gamma_kernel(int n, int ld, const double* __restrict__ W, double* __restrict__ out, CaseStrides cs) {
+    W = case_work_ptr(W, cs.work);
+    out = case_ptr(out, cs.out);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[(size_t)LLS_O_GAMMA * ld + i] = W[(size_t)W_X * ld + i];                     // scene.py:827
 }
 
 int launch_assemble_linear(Scene* s, cudaStream_t st) {
-    linear_rows_kernel<<<(s->n + 127) / 128, 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W);
+    linear_rows_kernel<<<dim3((s->n + 127) / 128, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, strides(s, false));
     count_launch();
-    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS);
-    assemble_kernel<false><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M);
+    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS, s->ncases);
+    assemble_kernel<false><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M, strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }
 
-int launch_residual(Scene* s, int vel_only, cudaStream_t st) {
-    residual_kernel<128><<<s->n, 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial, vel_only);
+int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked) {
+    residual_kernel<128><<<dim3(s->n, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
+                                                                  vel_only, strides(s, masked));
     count_launch();
     if (!vel_only) {
-        sum_kernel<<<1, 256, 0, st>>>(s->n, s->partial, s->scalars, 0);
+        sum_kernel<<<dim3(1, 1, s->ncases), 256, 0, st>>>(s->n, s->partial, s->scalars, 0, strides(s, masked));
         count_launch();
     }
     LLS_CUDA_TRY(cudaGetLastError());
@@ -241,21 +264,54 @@ int launch_residual(Scene* s, int vel_only, cudaStream_t st) {
 }
 
 int launch_assemble_jacobian(Scene* s, cudaStream_t st) {
-    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS);
-    assemble_kernel<true><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M);
+    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS, s->ncases);
+    assemble_kernel<true><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M, strides(s, true));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }
 
 int launch_newton_update(Scene* s, double relaxation, cudaStream_t st) {
+    dim3 grid((s->n + 127) / 128, 1, s->ncases);
     if (relaxation < 0.0) {
-        copy_gamma_kernel<<<(s->n + 127) / 128, 128, 0, st>>>(s->n, s->ld, s->W, s->out);
+        copy_gamma_kernel<<<grid, 128, 0, st>>>(s->n, s->ld, s->W, s->out, strides(s, false));
         count_launch();
     } else {
-        newton_update_kernel<<<(s->n + 127) / 128, 128, 0, st>>>(s->n, s->ld, relaxation, s->W, s->out);
+        newton_update_kernel<<<grid, 128, 0, st>>>(s->n, s->ld, relaxation, s->W, s->out, strides(s, true));
         count_launch();
     }
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch control: which cases take part in Newton iteration k (reference loop test `while error > convergence`,
+// scene.py:853; error of iteration 0 is 100, scene.py:852), their iteration counters and the number still active
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) newton_control_kernel(int ncases, int k, double convergence, const double* __restrict__ scalars,
+                                                             size_t work_stride, int* __restrict__ ctl) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncases) return;
+    int* active = ctl;
+    int* iters = ctl + ncases;
+    int a = 1;
+    if (k > 1) {
+        const double err2 = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(scalars) + (size_t)c * work_stride);
+        a = active[c] && (sqrt(err2) > convergence);   // NaN compares false: the case stops, like the reference's loop test
+    } else {
+        iters[c] = 0;
+    }
+    active[c] = a;
+    if (a) {
+        iters[c] = k;
+        atomicAdd(ctl + 2 * ncases, 1);
+    }
+}
+
+int launch_newton_control(Scene* s, int k, double convergence, cudaStream_t st) {
+    LLS_CUDA_TRY(cudaMemsetAsync(s->ctl + 2 * s->ncases, 0, sizeof(int), st));
+    newton_control_kernel<<<(s->ncases + 255) / 256, 256, 0, st>>>(s->ncases, k, convergence, s->scalars, s->cs.work, s->ctl);
+    count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }

@@ -9,7 +9,11 @@ namespace lls {
 __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                         const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                         const double* __restrict__ ac, double* __restrict__ W,
-                                                        double* __restrict__ out, int* __restrict__ status) {
+                                                        double* __restrict__ out, int* __restrict__ status, CaseStrides cs) {
+    ac = case_ptr(ac, cs.ac);
+    W = case_work_ptr(W, cs.work);
+    out = case_ptr(out, cs.out);
+    status = case_work_ptr(status, cs.work);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *status = 0;
     if (i >= ld) return;
@@ -66,7 +70,8 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
 
 int launch_flow_state(Scene* s, cudaStream_t st) {
     int block = 128, grid = (s->ld + block - 1) / block;
-    flow_state_kernel<<<grid, block, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->ac, s->W, s->out, s->status);
+    flow_state_kernel<<<dim3(grid, 1, s->ncases), block, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->ac, s->W, s->out, s->status,
+                                                                  strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;

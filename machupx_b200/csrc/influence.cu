@@ -96,7 +96,11 @@ __device__ __forceinline__ Vec3 joint_corner(const Vec3& Pe, const Vec3& tangent
 #endif
 __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kernel(
     int n, int ld, const double* __restrict__ tab, const int32_t* __restrict__ itab, const double* __restrict__ ac,
-    const double* __restrict__ out, double* __restrict__ V, double thr, int* __restrict__ status) {
+    const double* __restrict__ out, double* __restrict__ V, double thr, int* __restrict__ status, CaseStrides cs) {
+    ac = case_ptr(ac, cs.ac);
+    out = case_ptr(out, cs.out);
+    V = case_ptr(V, cs.V);
+    status = case_work_ptr(status, cs.work);
     __shared__ RowSmem rs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row0 = blockIdx.y * INF_ROWS;
@@ -234,8 +238,9 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
 
 int launch_influence(Scene* s, double impingement_threshold, cudaStream_t st) {
     const int windows = (s->ld + INF_OUT - 1) / INF_OUT;
-    dim3 grid((windows + INF_WARPS - 1) / INF_WARPS, (s->n + INF_ROWS - 1) / INF_ROWS);
-    influence_kernel<<<grid, INF_WARPS * 32, 0, st>>>(s->n, s->ld, s->tab, s->itab, s->ac, s->out, s->V, impingement_threshold, s->status);
+    dim3 grid((windows + INF_WARPS - 1) / INF_WARPS, (s->n + INF_ROWS - 1) / INF_ROWS, s->ncases);
+    influence_kernel<<<grid, INF_WARPS * 32, 0, st>>>(s->n, s->ld, s->tab, s->itab, s->ac, s->out, s->V, impingement_threshold, s->status,
+                                                      strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;

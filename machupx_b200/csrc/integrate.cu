@@ -8,7 +8,10 @@
 
 namespace lls {
 
-__global__ void __launch_bounds__(128) scale_gamma_pro_kernel(int n, int ld, const double* __restrict__ W, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) scale_gamma_pro_kernel(int n, int ld, const double* __restrict__ W, double* __restrict__ out,
+                                                              CaseStrides cs) {
+    W = case_work_ptr(W, cs.work);
+    out = case_ptr(out, cs.out);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double r = W[(size_t)W_VIR_MAG * ld + i] / W[(size_t)W_VINF_MAG * ld + i];   // scene.py:938-939
@@ -29,7 +32,10 @@ constexpr int INT_THREADS = 128;
 __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                                 const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                                 const double* __restrict__ W, double* __restrict__ out,
-                                                                double* __restrict__ seg_fm) {
+                                                                double* __restrict__ seg_fm, CaseStrides cs) {
+    W = case_work_ptr(W, cs.work);
+    out = case_ptr(out, cs.out);
+    seg_fm = case_ptr(seg_fm, cs.seg);
     const int s = blockIdx.x;
     const int32_t* segid = itab + (size_t)LLS_I_SEGMENT * ld;
     const int begin = lower_bound_seg(segid, n, s), end = lower_bound_seg(segid, n, s + 1);
@@ -119,14 +125,15 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
 }
 
 int launch_integrate(Scene* s, double* d_seg_fm, cudaStream_t st) {
-    integrate_kernel<<<s->n_seg, INT_THREADS, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out, d_seg_fm);
+    integrate_kernel<<<dim3(s->n_seg, 1, s->ncases), INT_THREADS, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out, d_seg_fm,
+                                                                           strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }
 
 int launch_scale_gamma_pro(Scene* s, cudaStream_t st) {
-    scale_gamma_pro_kernel<<<(s->n + 127) / 128, 128, 0, st>>>(s->n, s->ld, s->W, s->out);
+    scale_gamma_pro_kernel<<<dim3((s->n + 127) / 128, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->W, s->out, strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;

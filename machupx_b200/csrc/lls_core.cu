@@ -54,7 +54,7 @@ static int read_scalars(Scene* s, cudaStream_t st, int count) {
 using namespace lls;
 
 extern "C" const char* lls_last_error(void) { return lls::g_err; }
-extern "C" int lls_abi_version(void) { return 1; }
+extern "C" int lls_abi_version(void) { return 2; }
 extern "C" unsigned long long lls_launch_count(void) { return lls::g_launches; }
 
 extern "C" int lls_query_sizes(int n, int n_segments, lls_sizes* out) {
@@ -84,7 +84,8 @@ extern "C" int lls_create(lls_scene** out, int n, int n_aircraft, int n_segments
     h->n_seg = n_segments;
     h->n_af = n_airfoils;
     h->flags = flags;
-    if (cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) != cudaSuccess || cudaEventCreate(&h->ev[0]) != cudaSuccess ||
+    if (cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) != cudaSuccess || cudaMallocHost(&h->h_ctl, 16 * sizeof(int)) != cudaSuccess ||
+        cudaEventCreate(&h->ev[0]) != cudaSuccess ||
         cudaEventCreate(&h->ev[1]) != cudaSuccess) {
         set_last_error(__FILE__, __LINE__, "lls_create: CUDA resource creation failed (is a GPU visible?)");
         delete h;
@@ -97,6 +98,7 @@ extern "C" int lls_create(lls_scene** out, int n, int n_aircraft, int n_segments
 extern "C" int lls_destroy(lls_scene* h) {
     if (h == nullptr) return LLS_OK;
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->ev[0]) cudaEventDestroy(h->ev[0]);
     if (h->ev[1]) cudaEventDestroy(h->ev[1]);
     delete h;
@@ -133,6 +135,29 @@ extern "C" int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab
     // the LU's publish flags compare against a per-handle epoch that starts at 0: clear them once here
     LLS_CUDA_TRY(cudaMemset(h->lu_flags, 0, (size_t)2 * (h->ld / LU_NB + 1) * 4));
     h->lu_epoch = 0;
+    h->ncases = 1;
+    h->cs = CaseStrides();
+    h->ctl = nullptr;
+    return LLS_OK;
+}
+
+extern "C" int lls_bind_batch(lls_scene* h, int ncases, const double* d_tab, const int32_t* d_itab, const double* d_airfoils,
+                              double* d_out, double* d_vji, double* d_mat, void* d_work, size_t work_bytes_per_case, int* d_ctl) {
+    LLS_REQUIRE(h != nullptr && ncases >= 1 && ncases <= 65535, LLS_ERR_ARG, "lls_bind_batch: 1 <= ncases <= 65535 (case index is blockIdx.z)");
+    LLS_REQUIRE(d_ctl != nullptr, LLS_ERR_ARG, "lls_bind_batch: null control block");
+    LLS_REQUIRE(work_bytes_per_case % 256 == 0, LLS_ERR_ARG, "lls_bind_batch: work_bytes_per_case must be a multiple of 256");
+    LLS_TRY(lls_bind(h, d_tab, d_itab, d_airfoils, d_out, d_vji, d_mat, d_work, work_bytes_per_case));   // case 0 carves the layout
+    h->ncases = ncases;
+    h->cs.out = (size_t)LLS_NO * h->ld;
+    h->cs.V = (size_t)h->n * 3 * h->ld;
+    h->cs.M = (size_t)h->ld * h->ld;
+    h->cs.ac = (size_t)h->n_ac * LLS_AC_STRIDE;
+    h->cs.seg = (size_t)h->n_seg * 12;
+    h->cs.work = work_bytes_per_case;
+    h->ctl = d_ctl;
+    // LU publish flags of every case start below any epoch
+    LLS_CUDA_TRY(cudaMemset2D(h->lu_flags, work_bytes_per_case, 0, (size_t)2 * (h->ld / LU_NB + 1) * 4, (size_t)ncases));
+    LLS_CUDA_TRY(cudaMemset(d_ctl, 0, sizeof(int) * (2 * (size_t)ncases + 4)));
     return LLS_OK;
 }
 
@@ -175,6 +200,7 @@ extern "C" int lls_solve_nonlinear(lls_scene* h, double convergence, double rela
                                    int* iterations, double* final_error, int* status, double* err_hist) {
     LLS_CHECK_BOUND(h);
     LLS_REQUIRE(iterations && final_error && status, LLS_ERR_ARG, "lls_solve_nonlinear: null output");
+    LLS_REQUIRE(h->ncases == 1, LLS_ERR_STATE, "lls_solve_nonlinear: a batch is bound, use lls_solve_nonlinear_batch");
     cudaStream_t st = (cudaStream_t)stream;
     int it = 0;
     double error = 100.0;                                                        // scene.py:851-852
@@ -219,13 +245,66 @@ extern "C" int lls_solve_nonlinear(lls_scene* h, double convergence, double rela
     return LLS_OK;
 }
 
+extern "C" int lls_solve_nonlinear_batch(lls_scene* h, double convergence, double relaxation, int max_iterations, void* stream,
+                                         int* iterations, double* final_error, int* status) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(iterations && final_error && status, LLS_ERR_ARG, "lls_solve_nonlinear_batch: null output");
+    LLS_REQUIRE(h->ctl != nullptr, LLS_ERR_STATE, "lls_solve_nonlinear_batch: no batch bound (lls_bind_batch)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nc = h->ncases;
+    // Every case runs the reference's loop (scene.py:851-913) in lock step: iteration k is executed for the cases whose
+    // residual norm of iteration k-1 was above the threshold; kernels of masked-out cases return at once.
+    for (int k = 1; k <= max_iterations; ++k) {
+        LLS_TRY(launch_newton_control(h, k, convergence, st));
+        LLS_CUDA_TRY(cudaMemcpyAsync(h->h_ctl, h->ctl + 2 * nc, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LLS_CUDA_TRY(cudaStreamSynchronize(st));
+        if (h->h_ctl[0] == 0) break;
+        {
+            PhaseTimer t(h, st, 4);
+            LLS_TRY(launch_residual(h, 0, st, true));                            // scene.py:857-858
+        }
+        {
+            PhaseTimer t(h, st, 1);
+            LLS_TRY(launch_assemble_jacobian(h, st));                            // scene.py:862-893
+        }
+        {
+            PhaseTimer t(h, st, 2);
+            LLS_TRY(lu_factor_solve(h, h->M, wf(h, W_RHS), wf(h, W_X), st, true)); // scene.py:896
+        }
+        LLS_TRY(launch_newton_update(h, relaxation, st));                        // scene.py:899
+    }
+    {
+        PhaseTimer t(h, st, 4);
+        LLS_TRY(launch_residual(h, 0, st, false));                               // scene.py:906-907, 912-913
+    }
+    LLS_CUDA_TRY(cudaMemcpy2DAsync(final_error, sizeof(double), h->scalars, h->cs.work, sizeof(double), (size_t)nc, cudaMemcpyDeviceToHost, st));
+    LLS_CUDA_TRY(cudaMemcpyAsync(iterations, h->ctl + nc, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    LLS_CUDA_TRY(cudaMemcpy2DAsync(status, sizeof(int), h->status, h->cs.work, sizeof(int), (size_t)nc, cudaMemcpyDeviceToHost, st));
+    LLS_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int c = 0; c < nc; ++c) {
+        final_error[c] = sqrt(final_error[c]);
+        if (iterations[c] >= max_iterations) status[c] |= LLS_STATUS_NOT_CONVERGED;   // scene.py:905-908
+        if (!(final_error[c] == final_error[c])) status[c] |= LLS_STATUS_NAN;
+    }
+    return LLS_OK;
+}
+
+extern "C" int lls_get_status_batch(lls_scene* h, void* stream, int* status) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(status != nullptr, LLS_ERR_ARG, "lls_get_status_batch: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    LLS_CUDA_TRY(cudaMemcpy2DAsync(status, sizeof(int), h->status, h->cs.work, sizeof(int), (size_t)h->ncases, cudaMemcpyDeviceToHost, st));
+    LLS_CUDA_TRY(cudaStreamSynchronize(st));
+    return LLS_OK;
+}
+
 extern "C" int lls_integrate(lls_scene* h, double* d_seg_fm, void* stream) {
     LLS_CHECK_BOUND(h);
     LLS_REQUIRE(d_seg_fm != nullptr, LLS_ERR_ARG, "lls_integrate: null output");
     cudaStream_t st = (cudaStream_t)stream;
     PhaseTimer t(h, st, 5);
     if (h->flags & LLS_FLAG_MATCH_MACHUP_PRO) LLS_TRY(launch_scale_gamma_pro(h, st));   // scene.py:938-939
-    LLS_TRY(launch_residual(h, 1, st));                                          // v_i with the final gamma, scene.py:943
+    LLS_TRY(launch_residual(h, 1, st, false));                                   // v_i with the final gamma, scene.py:943
     return launch_integrate(h, d_seg_fm, st);
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <type_traits>
 #include "../../include/lls.h"
 
 #define LLS_CUDA_TRY(expr)                                                                    \
@@ -58,8 +59,28 @@ enum WField {
     W_NF = 26
 };
 
+// Batches: `ncases` independent flight states of ONE geometry (alpha / beta / rate / control sweeps) are solved by the same
+// launches with the case index in blockIdx.z.  Geometry tables are shared; every per-case buffer is the single-scene
+// buffer repeated with these element strides (all zero for a single scene).  `active` masks cases out of the Newton phase.
+struct CaseStrides {
+    size_t out = 0, V = 0, M = 0, ac = 0, seg = 0;   // doubles
+    size_t work = 0;                                  // BYTES between the work regions of consecutive cases
+    const int* active = nullptr;
+};
+template <class T>
+__device__ __forceinline__ T* case_ptr(T* p, size_t stride) { return p + (size_t)blockIdx.z * stride; }
+template <class T>
+__device__ __forceinline__ T* case_work_ptr(T* p, size_t stride_bytes) {
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(const_cast<typename std::remove_const<T>::type*>(p)) + (size_t)blockIdx.z * stride_bytes);
+}
+#define LLS_CASE_INACTIVE(cs) ((cs).active != nullptr && (cs).active[blockIdx.z] == 0)
+
 struct Scene {
     int n = 0, ld = 0, n_ac = 0, n_seg = 0, n_af = 0, flags = 0;
+    int ncases = 1;             // > 1 after lls_bind_batch
+    CaseStrides cs;             // strides of the bound batch (active == nullptr)
+    int* ctl = nullptr;         // batch control block (device): active[ncases], iterations[ncases], n_active
+    int* h_ctl = nullptr;       // pinned host mirror of n_active
     const double* tab = nullptr;
     const int32_t* itab = nullptr;
     const double* af = nullptr;
@@ -82,6 +103,11 @@ struct Scene {
     cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
+inline CaseStrides strides(const Scene* s, bool masked) {
+    CaseStrides c = s->cs;
+    c.active = (masked && s->ncases > 1) ? s->ctl : nullptr;
+    return c;
+}
 inline const double* tabf(const Scene* s, int f) { return s->tab + (size_t)f * s->ld; }
 inline const int32_t* itabf(const Scene* s, int f) { return s->itab + (size_t)f * s->ld; }
 inline double* outf(const Scene* s, int f) { return s->out + (size_t)f * s->ld; }
@@ -91,12 +117,13 @@ inline double* wf(const Scene* s, int f) { return s->W + (size_t)f * s->ld; }
 int launch_flow_state(Scene* s, cudaStream_t st);
 int launch_influence(Scene* s, double impingement_threshold, cudaStream_t st);
 int launch_assemble_linear(Scene* s, cudaStream_t st);
-int launch_residual(Scene* s, int vel_only, cudaStream_t st);  // matvec + section lift + R, ||R||^2 -> scalars[0]
+int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked = false);  // matvec + section lift + R, ||R||^2 -> scalars[0]
+int launch_newton_control(Scene* s, int k, double convergence, cudaStream_t st);      // batch: active mask / iteration counters of iteration k
 int launch_assemble_jacobian(Scene* s, cudaStream_t st);
 int launch_newton_update(Scene* s, double relaxation, cudaStream_t st);
 int launch_integrate(Scene* s, double* d_seg_fm, cudaStream_t st);
 int launch_scale_gamma_pro(Scene* s, cudaStream_t st);
-int lu_factor_solve(Scene* s, double* d_mat, double* d_rhs, double* d_x, cudaStream_t st);  // rhs may be null
+int lu_factor_solve(Scene* s, double* d_mat, double* d_rhs, double* d_x, cudaStream_t st, bool masked = false);  // rhs may be null
 int lu_solve_only(Scene* s, const double* d_mat, double* d_rhs_inout, cudaStream_t st);
 
 }  // namespace lls

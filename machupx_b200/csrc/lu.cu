@@ -302,7 +302,15 @@ template <bool FIRST>
 __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restrict__ M, int ld, int k, int rem,
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
-                                                                double* __restrict__ scalars, int* __restrict__ status) {
+                                                                double* __restrict__ scalars, int* __restrict__ status, CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    M = case_ptr(M, cs.M);
+    if (rhs != nullptr) rhs = case_work_ptr(rhs, cs.work);
+    dbuf = case_work_ptr(dbuf, cs.work);
+    uinv = case_work_ptr(uinv, cs.work);
+    flags = case_work_ptr(flags, cs.work);
+    scalars = case_work_ptr(scalars, cs.work);
+    status = case_work_ptr(status, cs.work);
     extern __shared__ __align__(16) double sm[];
     double* sA = sm;
     double* sB = sm + NB * TS;
@@ -467,7 +475,13 @@ constexpr int BS_THREADS = NB;
 __global__ void __launch_bounds__(BS_THREADS) lu_backsolve_chain_kernel(const double* __restrict__ M, int ld, int nblk,
                                                                         const double* __restrict__ uinv,
                                                                         const double* __restrict__ y, double* __restrict__ x,
-                                                                        int* __restrict__ xflags, int epoch) {
+                                                                        int* __restrict__ xflags, int epoch, CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    M = case_ptr(M, cs.M);
+    uinv = case_work_ptr(uinv, cs.work);
+    y = case_work_ptr(y, cs.work);
+    x = case_work_ptr(x, cs.work);
+    xflags = case_work_ptr(xflags, cs.work);
     __shared__ __align__(16) double sx[NB];
     const int t = threadIdx.x;
     const int bi = nblk - 1 - blockIdx.x;
@@ -581,30 +595,35 @@ int lu_solve_only(Scene* s, const double* M, double* rhs, cudaStream_t st) {
         lu_forwardsolve_kernel<<<nblk - k, NB, 0, st>>>(M, ld, k, rhs, y);
         count_launch();
     }
-    lu_backsolve_chain_kernel<<<nblk, BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, y, rhs, s->lu_flags + nblk + 1, ++s->lu_epoch);
+    lu_backsolve_chain_kernel<<<nblk, BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, y, rhs, s->lu_flags + nblk + 1, ++s->lu_epoch, CaseStrides());
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }
 
-int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st) {
+int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st, bool masked) {
     const int ld = s->ld, nblk = ld / NB;
+    // an external matrix (lls_lu_factor) is always a single case; the scene's own matrix follows the bound batch
+    const int ncases = (M == s->M) ? s->ncases : 1;
+    const CaseStrides cs = (M == s->M) ? strides(s, masked) : CaseStrides();
     LLS_TRY(lu_prepare(s));
     const int epoch = ++s->lu_epoch;
     double* dbuf = s->inv;          // 2 x PUB_DOUBLES published diagonal factors
     int* flags = s->lu_flags;
     {
         const int rem = nblk;       // block 0 and its panel
-        lu_step_kernel<true><<<2 * rem - 1, LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status);
+        lu_step_kernel<true><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch,
+                                                                                                 s->scalars, s->status, cs);
         count_launch();
     }
     for (int k = 0; k + 1 < nblk; ++k) {
         const int rem = nblk - 1 - k;
-        lu_step_kernel<false><<<rem * rem, LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status);
+        lu_step_kernel<false><<<dim3(rem * rem, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch,
+                                                                                               s->scalars, s->status, cs);
         count_launch();
     }
     if (rhs) {
-        lu_backsolve_chain_kernel<<<nblk, BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, rhs, x, s->lu_flags + nblk + 1, epoch);
+        lu_backsolve_chain_kernel<<<dim3(nblk, 1, ncases), BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, rhs, x, s->lu_flags + nblk + 1, epoch, cs);
         count_launch();
     }
     LLS_CUDA_TRY(cudaGetLastError());

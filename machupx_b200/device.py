@@ -167,3 +167,84 @@ class DeviceScene:
             _native.check(self.lib.lls_lu_solve(self.handle, _ptr(dA), _ptr(db), self._stream()))
             torch.cuda.synchronize(self.device)
         return db[:n].cpu().numpy(), dA.cpu().numpy()
+
+
+class BatchDeviceScene:
+    """``ncases`` flight states of one geometry solved by the same launches (lls_bind_batch): the device side of alpha /
+    beta / rate sweeps and of the finite-difference stencils of the derivative and trim drivers.  Geometry tables are
+    uploaded once; per case only the 12-double aircraft state block differs."""
+
+    def __init__(self, tables, ncases, device=None):
+        if not torch.cuda.is_available():
+            raise _native.LlsError("machupx_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _native.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.n, self.ld, self.ncases = int(tables["n"]), int(tables["ld"]), int(ncases)
+        self.n_aircraft, self.n_segments, self.flags = int(tables["n_aircraft"]), int(tables["n_segments"]), int(tables["flags"])
+        af = np.ascontiguousarray(tables["airfoils"], dtype=np.float64).reshape(-1, L.AF_STRIDE)
+        self.n_airfoils = af.shape[0]
+        sizes = _native.Sizes()
+        _native.check(self.lib.lls_query_sizes(self.n, self.n_segments, ctypes.byref(sizes)))
+        self.work_stride = (int(sizes.work_bytes) + 255) // 256 * 256
+        nc, dev = self.ncases, self.device
+        with torch.cuda.device(dev):
+            self.handle = ctypes.c_void_p()
+            _native.check(self.lib.lls_create(ctypes.byref(self.handle), self.n, self.n_aircraft, self.n_segments, self.n_airfoils, self.flags))
+            self.d_tab = torch.from_numpy(np.ascontiguousarray(tables["tab"], dtype=np.float64)).to(dev)
+            self.d_itab = torch.from_numpy(np.ascontiguousarray(tables["itab"], dtype=np.int32)).to(dev)
+            self.d_af = torch.from_numpy(af).to(dev)
+            self.d_out = torch.zeros((nc, L.NO, self.ld), dtype=torch.float64, device=dev)
+            self.d_V = torch.empty((nc, self.n, 3, self.ld), dtype=torch.float64, device=dev)
+            self.d_M = torch.empty((nc, self.ld, self.ld), dtype=torch.float64, device=dev)
+            self.d_work = torch.zeros((nc, self.work_stride), dtype=torch.uint8, device=dev)
+            self.d_ctl = torch.zeros(2 * nc + 4, dtype=torch.int32, device=dev)
+            self.d_ac = torch.zeros((nc, self.n_aircraft, L.AC_STRIDE), dtype=torch.float64, device=dev)
+            self.d_seg_fm = torch.zeros((nc, self.n_segments, 12), dtype=torch.float64, device=dev)
+            self.h_ac = torch.zeros((nc, self.n_aircraft, L.AC_STRIDE), dtype=torch.float64).pin_memory()
+            self.h_seg_fm = torch.zeros((nc, self.n_segments, 12), dtype=torch.float64).pin_memory()
+            _native.check(self.lib.lls_bind_batch(self.handle, nc, _ptr(self.d_tab), _ptr(self.d_itab), _ptr(self.d_af), _ptr(self.d_out),
+                                                  _ptr(self.d_V), _ptr(self.d_M), _ptr(self.d_work), ctypes.c_size_t(self.work_stride),
+                                                  _ptr(self.d_ctl)))
+            _native.check(self.lib.lls_set_state(self.handle, _ptr(self.d_ac)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.lls_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def upload_states(self, ac_states):
+        self.h_ac.copy_(torch.from_numpy(np.ascontiguousarray(ac_states, dtype=np.float64).reshape(self.ncases, self.n_aircraft, L.AC_STRIDE)))
+        self.d_ac.copy_(self.h_ac, non_blocking=True)
+
+    def solve(self, solver_type, convergence, relaxation, max_iterations, impingement_threshold=1e-10, linear_start=True):
+        """flow state + influence build + linear solve (+ Newton) + integration for every case.
+        Returns (seg_fm (ncases, n_segments, 12) numpy, iterations, final_error, status)."""
+        nc = self.ncases
+        its = (ctypes.c_int * nc)()
+        err = (ctypes.c_double * nc)()
+        status = (ctypes.c_int * nc)()
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            _native.check(self.lib.lls_flow_state(self.handle, st))
+            _native.check(self.lib.lls_build_influence(self.handle, float(impingement_threshold), st))
+            if solver_type == "linear" or linear_start:
+                _native.check(self.lib.lls_solve_linear(self.handle, st))
+            if solver_type == "nonlinear":
+                _native.check(self.lib.lls_solve_nonlinear_batch(self.handle, float(convergence), float(relaxation), int(max_iterations), st,
+                                                                 its, err, status))
+            else:
+                _native.check(self.lib.lls_get_status_batch(self.handle, st, status))
+            _native.check(self.lib.lls_integrate(self.handle, _ptr(self.d_seg_fm), st))
+            self.h_seg_fm.copy_(self.d_seg_fm, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return (self.h_seg_fm.numpy().copy(), np.frombuffer(its, dtype=np.int32).copy(), np.frombuffer(err, dtype=np.float64).copy(),
+                np.frombuffer(status, dtype=np.int32).copy())
+
+    def gamma(self):
+        return self.d_out[:, L.O_GAMMA, :self.n].cpu().numpy()

@@ -132,3 +132,43 @@ def assemble_fm(seg_fm, frames, non_dimensional=True, dimensional=True, report_b
                     entry["total"][k] = float(x) * sc
         FM[fr.name] = entry
     return FM
+
+
+def batch_totals(seg_fm, ac_states, aircraft):
+    """Aircraft totals of a batch of flight states without building per-case dictionaries.
+
+    seg_fm: (ncases, n_segments, 12) earth-axes segment sums from the device; ac_states: (ncases, n_aircraft, AC_STRIDE)
+    state blocks the cases were solved with; aircraft: list of dicts with keys name, q, wind, rho, S_w, l_ref_lat,
+    l_ref_lon, seg_range (start, stop).  Returns {name: {key: ndarray(ncases)}} with the body- and wind-frame
+    coefficients and dimensional loads of ``Scene._FM[name]["total"]`` (scene.py:1078-1129, 1238-1406)."""
+    from . import layout as L
+    from .rotations import rotation_matrix
+    seg_fm = np.asarray(seg_fm, dtype=float)
+    out = {}
+    for ia, ac in enumerate(aircraft):
+        r0, r1 = ac["seg_range"]
+        tot = seg_fm[:, r0:r1, :].sum(axis=1)                      # (ncases, 12)
+        F_e = tot[:, 0:3] + tot[:, 6:9]
+        M_e = tot[:, 3:6] + tot[:, 9:12]
+        C = rotation_matrix(ac["q"])                                # v_body = C v_earth
+        F_b, M_b = F_e @ C.T, M_e @ C.T
+        v_inf = ac_states[:, ia, L.AC_VTRANS:L.AC_VTRANS + 3] + np.asarray(ac["wind"], dtype=float)[np.newaxis, :]
+        V = np.linalg.norm(v_inf, axis=1)
+        u_inf = (v_inf / V[:, np.newaxis]) @ C.T
+        y = np.array([0.0, 1.0, 0.0])
+        u_lift = np.cross(u_inf, y)
+        u_lift /= np.linalg.norm(u_lift, axis=1, keepdims=True)
+        u_side = np.cross(u_lift, u_inf)
+        u_side /= np.linalg.norm(u_side, axis=1, keepdims=True)
+        dot = lambda a, b: np.einsum("ij,ij->i", a, b)
+        nd = 2.0 / (float(ac["rho"]) * V * V * ac["S_w"])
+        nd_lat, nd_lon = nd / ac["l_ref_lat"], nd / ac["l_ref_lon"]
+        d = {"Fx": F_b[:, 0], "Fy": F_b[:, 1], "Fz": F_b[:, 2], "Mx": M_b[:, 0], "My": M_b[:, 1], "Mz": M_b[:, 2],
+             "FD": dot(F_b, u_inf), "FS": dot(F_b, u_side), "FL": dot(F_b, u_lift),
+             "Mx_w": dot(M_b, u_inf), "My_w": dot(M_b, u_side), "Mz_w": dot(M_b, u_lift)}
+        d.update({"Cx": d["Fx"] * nd, "Cy": d["Fy"] * nd, "Cz": d["Fz"] * nd,
+                  "Cl": d["Mx"] * nd_lat, "Cm": d["My"] * nd_lon, "Cn": d["Mz"] * nd_lat,
+                  "CD": d["FD"] * nd, "CS": d["FS"] * nd, "CL": d["FL"] * nd,
+                  "Cl_w": d["Mx_w"] * nd_lat, "Cm_w": d["My_w"] * nd_lon, "Cn_w": d["Mz_w"] * nd_lat})
+        out[ac["name"]] = d
+    return out

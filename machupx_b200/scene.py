@@ -377,6 +377,71 @@ class Scene:
         self._solved = True
         return self._FM
 
+    def solve_forces_batch(self, states, aircraft=None, max_batch=4096):
+        """Solves a list of flight states of ONE aircraft of the scene in a single batched device pass (SURVEY.md section 8e
+        row 1; BASELINE.json configs[2]): the reference's idiom is a Python loop of set_aircraft_state + solve_forces.
+
+        ``states`` are state dictionaries as accepted by ``set_aircraft_state``; they may change velocity / alpha / beta /
+        angular rates but must keep the position and orientation the scene currently has (the geometry tables are shared
+        by all cases).  Returns {"totals": {aircraft_name: {key: ndarray(ncases)}}, "iterations", "final_error",
+        "converged", "status"}.  The aircraft states of the scene are left untouched."""
+        from .device import BatchDeviceScene
+        from .forces import batch_totals
+        if self._num_aircraft == 0:
+            raise RuntimeError("There are no aircraft in this scene. No calculations can be performed.")
+        name = self._only_aircraft(aircraft)
+        ap = self._airplanes[name]
+        if self._current_pose_key() != self._pose_key:
+            self._perform_geometry_and_atmos_calcs()
+        saved = ap.get_state()
+        saved_frame = ap.angular_rate_frame
+        pose = (np.array(ap.p_bar, dtype=float), np.array(ap.q, dtype=float))
+        rows = []
+        try:
+            for st in states:
+                position = np.array(st.get("position", [0.0, 0.0, 0.0]))
+                ap.set_state(**st, v_wind=self._get_wind(position))
+                if not (np.allclose(ap.p_bar, pose[0], rtol=0, atol=0) and np.allclose(ap.q, pose[1], rtol=0, atol=1e-15)):
+                    raise ValueError("solve_forces_batch: every state must keep the scene's current position and orientation")
+                rows.append(build_aircraft_state(self))
+        finally:
+            ap.v, ap.w, ap.p_bar, ap.q = saved
+            ap.angular_rate_frame = saved_frame
+        ac_states = np.array(rows)
+        n_total = len(states)
+        info = []
+        seg0 = 0
+        for a in self._airplane_objects:
+            info.append({"name": a.name, "q": a.q, "wind": self._get_wind(a.p_bar), "rho": self._get_density(a.p_bar), "S_w": a.S_w,
+                         "l_ref_lat": a.l_ref_lat, "l_ref_lon": a.l_ref_lon, "seg_range": (seg0, seg0 + len(a.segments))})
+            seg0 += len(a.segments)
+        seg_fm = np.zeros((n_total, self._tables["n_segments"], 12))
+        its, err, status = np.zeros(n_total, dtype=int), np.zeros(n_total), np.zeros(n_total, dtype=int)
+        for lo in range(0, n_total, max_batch):
+            hi = min(lo + max_batch, n_total)
+            nc = hi - lo
+            dev = getattr(self, "_batch_device", None)
+            if dev is None or dev.ncases != nc or dev.n != self._N or dev.flags != self._tables["flags"]:
+                dev = self._batch_device = BatchDeviceScene(self._tables, nc)
+                self._batch_tables_id = id(self._tables)
+            elif self._batch_tables_id != id(self._tables):
+                dev.d_tab.copy_(__import__("torch").from_numpy(np.ascontiguousarray(self._tables["tab"])))
+                self._batch_tables_id = id(self._tables)
+            dev.upload_states(ac_states[lo:hi])
+            seg_fm[lo:hi], its[lo:hi], err[lo:hi], status[lo:hi] = dev.solve(
+                self._solver_type, self._solver_convergence, self._solver_relaxation, self._max_solver_iterations,
+                self._impingement_threshold)
+        if (status & L.STATUS_IMPINGEMENT).any():
+            warnings.warn(_IMPINGEMENT_TEXT)
+        converged = (status & L.STATUS_NOT_CONVERGED) == 0
+        if not converged.all():
+            try:
+                raise SolverNotConvergedError(self._solver_type, float(err[~converged].max()))
+            except SolverNotConvergedError as e:
+                self._handle_error(e)
+        return {"totals": batch_totals(seg_fm, ac_states, info), "iterations": its, "final_error": err, "converged": converged,
+                "status": status, "seg_fm": seg_fm}
+
     def _frames(self):
         return [AircraftFrame(ap.name, ap.q, ap.v, self._get_wind(ap.p_bar), self._get_density(ap.p_bar), ap.S_w,
                               ap.l_ref_lat, ap.l_ref_lon, [seg.name for seg in ap.segments]) for ap in self._airplane_objects]
