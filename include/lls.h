@@ -188,6 +188,32 @@ int lls_solve_nonlinear_batch(lls_scene* h, double convergence, double relaxatio
 /* Status bits of every case of the bound batch (host array, ncases entries). */
 int lls_get_status_batch(lls_scene* h, void* stream, int* status);
 
+/* ---- one large scene partitioned by rows over the GPUs of one box ------------------------
+ * The reference holds V_ji (24 N^2 B) and J (8 N^2 B) in one address space and cannot run N >= ~9k at all; here the rows
+ * of V_ji / A / J are dealt to the ranks in 64-row blocks, round-robin (owner of block b = b mod world), and stored
+ * consecutively on their owner.  Per-point tables, gamma, the right-hand side and x stay replicated (O(N)).
+ * The library issues no collective itself: the host (torch.distributed / NCCL) broadcasts the per-step buffer of the LU,
+ * all-reduces the residual norm and the segment sums, and broadcasts each 64-value block of x in the back substitution.
+ *   lls_query_sizes_partitioned : buffer sizes per rank (ld = n rounded up to 64 * world)
+ *   lls_set_partition           : after lls_create, before lls_bind
+ *   lls_flow_state / lls_build_influence / lls_integrate : act on the rows this rank owns
+ *   lls_dist_assemble (newton = 0: A, b of scene.py:811-824; 1: Jacobian of scene.py:862-893), lls_dist_residual (local sum of
+ *   R_i^2), lls_dist_update_gamma (relaxation < 0: gamma = x), lls_dist_vectors (device pointers of rhs, x, gamma)
+ *   LU block step k:  owner(k) calls lls_dist_lu_owner -> step buffer [diag image | y_k | U tiles], host broadcasts
+ *   lls_dist_lu_step_doubles(k) doubles of it, every rank calls lls_dist_lu_update; then for k = last..0 the owner calls
+ *   lls_dist_back and the host broadcasts x[64 k .. 64 k + 63]. */
+int lls_query_sizes_partitioned(int n, int n_segments, int world, lls_sizes* out);
+int lls_set_partition(lls_scene* h, int world, int rank);
+int lls_dist_assemble(lls_scene* h, int newton, void* stream);
+int lls_dist_residual(lls_scene* h, void* stream, double* local_sum);
+int lls_dist_update_gamma(lls_scene* h, double relaxation, void* stream);
+int lls_dist_vectors(lls_scene* h, double** d_rhs, double** d_x, double** d_gamma);
+int lls_dist_lu_begin(lls_scene* h, size_t* max_step_doubles);
+int lls_dist_lu_step_doubles(lls_scene* h, int k, size_t* doubles);
+int lls_dist_lu_owner(lls_scene* h, int k, int with_rhs, double* d_step, void* stream);
+int lls_dist_lu_update(lls_scene* h, int k, int with_rhs, const double* d_step, void* stream);
+int lls_dist_back(lls_scene* h, int k, void* stream);
+
 /* Per-aircraft flight state, n_aircraft * LLS_AC_STRIDE doubles on the device
  * (reference: Airplane.set_state airplane.py:105-213 -> scene.py:562-582). */
 int lls_set_state(lls_scene* h, const double* d_ac_state);

@@ -32,6 +32,17 @@ SIGNATURES = {
     "lls_bind_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "lls_solve_nonlinear_batch": (_i, [_vp, _d, _d, _i, _vp, _pi, _pd, _pi]),
     "lls_get_status_batch": (_i, [_vp, _vp, _pi]),
+    "lls_query_sizes_partitioned": (_i, [_i, _i, _i, ctypes.POINTER(Sizes)]),
+    "lls_set_partition": (_i, [_vp, _i, _i]),
+    "lls_dist_assemble": (_i, [_vp, _i, _vp]),
+    "lls_dist_residual": (_i, [_vp, _vp, _pd]),
+    "lls_dist_update_gamma": (_i, [_vp, _d, _vp]),
+    "lls_dist_vectors": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "lls_dist_lu_begin": (_i, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
+    "lls_dist_lu_step_doubles": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_size_t)]),
+    "lls_dist_lu_owner": (_i, [_vp, _i, _i, _vp, _vp]),
+    "lls_dist_lu_update": (_i, [_vp, _i, _i, _vp, _vp]),
+    "lls_dist_back": (_i, [_vp, _i, _vp]),
     "lls_set_state": (_i, [_vp, _vp]),
     "lls_flow_state": (_i, [_vp, _vp]),
     "lls_build_influence": (_i, [_vp, _d, _vp]),

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(int n, int ld, int flags,
     V = case_ptr(V, cs.V);
     M = case_ptr(M, cs.M);
     __shared__ double sg[3][ASM_ROWS], sws[3][ASM_ROWS], se[3][ASM_ROWS], sdiag[ASM_ROWS];
-    const int row0 = blockIdx.y * ASM_ROWS;
+    const int lrow0 = blockIdx.y * ASM_ROWS;          // local (this rank's V / M) and global first row of the chunk
+    const int row0 = global_row(cs, lrow0);
     if (threadIdx.x < ASM_ROWS) {
         const int i = row0 + threadIdx.x;
         const bool ok = i < n;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(int n, int ld, int flags,
         if (i >= ld) break;
         double m;
         if (i < n) {
-            const double* v = V + (size_t)i * 3 * ld + j;
+            const double* v = V + (size_t)(lrow0 + r) * 3 * ld + j;
             Vec3 vt{v[0], v[(size_t)ld], v[(size_t)2 * ld]};
             const Vec3 g{sg[0][r], sg[1][r], sg[2][r]};
             if (NEWTON) {
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(int n, int ld, int flags,
         } else {
             m = (i == j) ? 1.0 : 0.0;
         }
-        M[(size_t)i * ld + j] = m;
+        M[(size_t)(lrow0 + r) * ld + j] = m;
     }
 }
 
@@ -117,11 +118,13 @@ __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int fl
     W = case_work_ptr(W, cs.work);
     out = case_ptr(out, cs.out);
     partial = case_work_ptr(partial, cs.work);
-    const int i = blockIdx.x;
+    const int li = blockIdx.x;                        // row of this rank's V
+    const int i = global_row(cs, li);
+    if (i >= n) return;
     const double* gamma = out + (size_t)LLS_O_GAMMA * ld;
-    const double2* v0 = reinterpret_cast<const double2*>(V + (size_t)i * 3 * ld);
-    const double2* v1 = reinterpret_cast<const double2*>(V + (size_t)i * 3 * ld + ld);
-    const double2* v2 = reinterpret_cast<const double2*>(V + (size_t)i * 3 * ld + 2 * (size_t)ld);
+    const double2* v0 = reinterpret_cast<const double2*>(V + (size_t)li * 3 * ld);
+    const double2* v1 = reinterpret_cast<const double2*>(V + (size_t)li * 3 * ld + ld);
+    const double2* v2 = reinterpret_cast<const double2*>(V + (size_t)li * 3 * ld + 2 * (size_t)ld);
     const double2* g2 = reinterpret_cast<const double2*>(gamma);
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int j = threadIdx.x; j < ld / 2; j += THREADS) {
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(256) sum_kernel(int n, const double* __restric
     scalars = case_work_ptr(scalars, cs.work);
     __shared__ double red[8];
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    for (int i = threadIdx.x; i < n; i += 256)
+        if (owns_row(cs, i)) s += partial[i];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(128) copy_gamma_kernel(int n, int ld, const do
 int launch_assemble_linear(Scene* s, cudaStream_t st) {
     linear_rows_kernel<<<dim3((s->n + 127) / 128, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, strides(s, false));
     count_launch();
-    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS, s->ncases);
+    dim3 grid((s->ld + 255) / 256, s->n_loc_blocks * (64 / ASM_ROWS), s->ncases);
     assemble_kernel<false><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M, strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
@@ -252,7 +256,7 @@ int launch_assemble_linear(Scene* s, cudaStream_t st) {
 }
 
 int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked) {
-    residual_kernel<128><<<dim3(s->n, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
+    residual_kernel<128><<<dim3(s->cs.P == 1 ? s->n : s->n_loc_blocks * 64, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
                                                                   vel_only, strides(s, masked));
     count_launch();
     if (!vel_only) {
@@ -264,7 +268,7 @@ int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked) {
 }
 
 int launch_assemble_jacobian(Scene* s, cudaStream_t st) {
-    dim3 grid((s->ld + 255) / 256, (s->ld + ASM_ROWS - 1) / ASM_ROWS, s->ncases);
+    dim3 grid((s->ld + 255) / 256, s->n_loc_blocks * (64 / ASM_ROWS), s->ncases);
     assemble_kernel<true><<<grid, 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->W, s->V, s->M, strides(s, true));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());

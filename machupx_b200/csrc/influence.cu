@@ -103,8 +103,11 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
     status = case_work_ptr(status, cs.work);
     __shared__ RowSmem rs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row0 = blockIdx.y * INF_ROWS;
+    static_assert(INF_ROWS == 64, "a chunk of control points is one 64-row block of the row partition");
+    const int lrow0 = blockIdx.y * INF_ROWS;          // first row of the chunk in this rank's V
+    const int row0 = global_row(cs, lrow0);           // ... and in the scene
     const int nrows = min(INF_ROWS, n - row0);
+    if (nrows <= 0) return;
 
     // stage the row constants of this chunk
     for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
         v = v + trailing_term(u0, r0j, r0jm, -1.0, thr, imp) + trailing_term(u1, r1j, r1jm, 1.0, thr, imp);
         if (!j_real) v = Vec3{0.0, 0.0, 0.0};
         if (writes) {
-            double* row = V + (size_t)i * 3 * ld + j_raw;
+            double* row = V + (size_t)(lrow0 + r) * 3 * ld + j_raw;
             row[0] = inv4pi * v.x;
             row[(size_t)ld] = inv4pi * v.y;
             row[(size_t)2 * ld] = inv4pi * v.z;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
 
 int launch_influence(Scene* s, double impingement_threshold, cudaStream_t st) {
     const int windows = (s->ld + INF_OUT - 1) / INF_OUT;
-    dim3 grid((windows + INF_WARPS - 1) / INF_WARPS, (s->n + INF_ROWS - 1) / INF_ROWS, s->ncases);
+    dim3 grid((windows + INF_WARPS - 1) / INF_WARPS, s->n_loc_blocks, s->ncases);
     influence_kernel<<<grid, INF_WARPS * 32, 0, st>>>(s->n, s->ld, s->tab, s->itab, s->ac, s->out, s->V, impingement_threshold, s->status,
                                                       strides(s, false));
     count_launch();

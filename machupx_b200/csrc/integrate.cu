@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
     for (int c = 0; c < 12; ++c) acc[c] = 0.0;
 
     for (int i = begin + threadIdx.x; i < end; i += INT_THREADS) {
+        if (!owns_row(cs, i)) continue;               // row-partitioned scene: the other ranks add their rows (all-reduce on the host side)
         const Vec3 vi = ld3(out, ld, LLS_O_VI, i);                                   // scene.py:943
         const double Vi2 = dot(vi, vi), Vi = sqrt(Vi2);                              // scene.py:944-946
         const Vec3 us = ld3(tab, ld, LLS_F_US, i), ua = ld3(tab, ld, LLS_F_UA, i), un = ld3(tab, ld, LLS_F_UN, i);

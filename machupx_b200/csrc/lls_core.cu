@@ -71,6 +71,31 @@ extern "C" int lls_query_sizes(int n, int n_segments, lls_sizes* out) {
     return LLS_OK;
 }
 
+extern "C" int lls_query_sizes_partitioned(int n, int n_segments, int world, lls_sizes* out) {
+    LLS_REQUIRE(n > 0 && out != nullptr && world >= 1, LLS_ERR_ARG, "lls_query_sizes_partitioned: bad arguments");
+    (void)n_segments;
+    const size_t ld = align_up((size_t)n, (size_t)LD_ALIGN * world);     // every rank owns the same number of 64-row blocks
+    const size_t local_rows = ld / world;
+    out->ld = ld;
+    out->tab_bytes = (size_t)LLS_NF * ld * 8;
+    out->itab_bytes = (size_t)LLS_NI * ld * 4;
+    out->out_bytes = (size_t)LLS_NO * ld * 8;
+    out->vji_bytes = local_rows * 3 * ld * 8;
+    out->mat_bytes = local_rows * ld * 8;
+    out->work_bytes = work_bytes_for((int)ld);
+    return LLS_OK;
+}
+
+extern "C" int lls_set_partition(lls_scene* h, int world, int rank) {
+    LLS_REQUIRE(h != nullptr && world >= 1 && rank >= 0 && rank < world, LLS_ERR_ARG, "lls_set_partition: bad arguments");
+    LLS_REQUIRE(h->tab == nullptr, LLS_ERR_STATE, "lls_set_partition: call it before lls_bind");
+    h->ld = (int)align_up((size_t)h->n, (size_t)LD_ALIGN * world);
+    h->n_loc_blocks = h->ld / LU_NB / world;
+    h->cs.P = world;
+    h->cs.rank = rank;
+    return LLS_OK;
+}
+
 extern "C" int lls_create(lls_scene** out, int n, int n_aircraft, int n_segments, int n_airfoils, int flags) {
     LLS_REQUIRE(out != nullptr && n > 0 && n_aircraft > 0 && n_segments > 0 && n_airfoils > 0, LLS_ERR_ARG, "lls_create: bad arguments");
     const bool total = flags & LLS_FLAG_TOTAL_VELOCITY, pro = flags & LLS_FLAG_MATCH_MACHUP_PRO;
@@ -80,6 +105,7 @@ extern "C" int lls_create(lls_scene** out, int n, int n_aircraft, int n_segments
     LLS_REQUIRE(h != nullptr, LLS_ERR_ARG, "lls_create: out of host memory");
     h->n = n;
     h->ld = (int)align_up((size_t)n, LD_ALIGN);
+    h->n_loc_blocks = h->ld / LU_NB;
     h->n_ac = n_aircraft;
     h->n_seg = n_segments;
     h->n_af = n_airfoils;
@@ -135,8 +161,14 @@ extern "C" int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab
     // the LU's publish flags compare against a per-handle epoch that starts at 0: clear them once here
     LLS_CUDA_TRY(cudaMemset(h->lu_flags, 0, (size_t)2 * (h->ld / LU_NB + 1) * 4));
     h->lu_epoch = 0;
+    LLS_CUDA_TRY(cudaMemset(h->inv, 0, LU_PUB_BYTES));       // includes the accumulator / ticket of the partitioned back substitution
     h->ncases = 1;
-    h->cs = CaseStrides();
+    {
+        const int P = h->cs.P, rank = h->cs.rank;
+        h->cs = CaseStrides();
+        h->cs.P = P;
+        h->cs.rank = rank;
+    }
     h->ctl = nullptr;
     return LLS_OK;
 }
@@ -144,6 +176,7 @@ extern "C" int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab
 extern "C" int lls_bind_batch(lls_scene* h, int ncases, const double* d_tab, const int32_t* d_itab, const double* d_airfoils,
                               double* d_out, double* d_vji, double* d_mat, void* d_work, size_t work_bytes_per_case, int* d_ctl) {
     LLS_REQUIRE(h != nullptr && ncases >= 1 && ncases <= 65535, LLS_ERR_ARG, "lls_bind_batch: 1 <= ncases <= 65535 (case index is blockIdx.z)");
+    LLS_REQUIRE(h->cs.P == 1, LLS_ERR_STATE, "lls_bind_batch: batches and row partitions do not combine");
     LLS_REQUIRE(d_ctl != nullptr, LLS_ERR_ARG, "lls_bind_batch: null control block");
     LLS_REQUIRE(work_bytes_per_case % 256 == 0, LLS_ERR_ARG, "lls_bind_batch: work_bytes_per_case must be a multiple of 256");
     LLS_TRY(lls_bind(h, d_tab, d_itab, d_airfoils, d_out, d_vji, d_mat, d_work, work_bytes_per_case));   // case 0 carves the layout
@@ -306,6 +339,78 @@ extern "C" int lls_integrate(lls_scene* h, double* d_seg_fm, void* stream) {
     if (h->flags & LLS_FLAG_MATCH_MACHUP_PRO) LLS_TRY(launch_scale_gamma_pro(h, st));   // scene.py:938-939
     LLS_TRY(launch_residual(h, 1, st, false));                                   // v_i with the final gamma, scene.py:943
     return launch_integrate(h, d_seg_fm, st);
+}
+
+// ---- one large scene, rows partitioned over the GPUs of a box: the solve in steps, collectives owned by the host ------
+#define LLS_CHECK_PART(h) LLS_REQUIRE((h)->ncases == 1, LLS_ERR_STATE, "partitioned entry points need a single scene")
+
+extern "C" int lls_dist_assemble(lls_scene* h, int newton, void* stream) {
+    LLS_CHECK_BOUND(h);
+    LLS_CHECK_PART(h);
+    PhaseTimer t(h, (cudaStream_t)stream, 1);
+    return newton ? launch_assemble_jacobian(h, (cudaStream_t)stream) : launch_assemble_linear(h, (cudaStream_t)stream);
+}
+
+extern "C" int lls_dist_residual(lls_scene* h, void* stream, double* local_sum) {
+    LLS_CHECK_BOUND(h);
+    LLS_CHECK_PART(h);
+    LLS_REQUIRE(local_sum != nullptr, LLS_ERR_ARG, "lls_dist_residual: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        PhaseTimer t(h, st, 4);
+        LLS_TRY(launch_residual(h, 0, st, false));
+    }
+    LLS_TRY(read_scalars(h, st, 1));
+    *local_sum = h->h_pinned[0];        // sum of R_i^2 over the rows this rank owns
+    return LLS_OK;
+}
+
+extern "C" int lls_dist_update_gamma(lls_scene* h, double relaxation, void* stream) {
+    LLS_CHECK_BOUND(h);
+    LLS_CHECK_PART(h);
+    return launch_newton_update(h, relaxation, (cudaStream_t)stream);
+}
+
+extern "C" int lls_dist_vectors(lls_scene* h, double** d_rhs, double** d_x, double** d_gamma) {
+    LLS_CHECK_BOUND(h);
+    if (d_rhs) *d_rhs = wf(h, W_RHS);
+    if (d_x) *d_x = wf(h, W_X);
+    if (d_gamma) *d_gamma = outf(h, LLS_O_GAMMA);
+    return LLS_OK;
+}
+
+extern "C" int lls_dist_lu_begin(lls_scene* h, size_t* max_step_doubles) {
+    LLS_CHECK_BOUND(h);
+    LLS_CHECK_PART(h);
+    if (max_step_doubles) *max_step_doubles = lu_dist_step_doubles(h, 0);
+    return lu_dist_begin(h);
+}
+
+extern "C" int lls_dist_lu_step_doubles(lls_scene* h, int k, size_t* doubles) {
+    LLS_REQUIRE(h != nullptr && doubles != nullptr && k >= 0 && k < h->ld / LU_NB, LLS_ERR_ARG, "lls_dist_lu_step_doubles: bad arguments");
+    *doubles = lu_dist_step_doubles(h, k);
+    return LLS_OK;
+}
+
+extern "C" int lls_dist_lu_owner(lls_scene* h, int k, int with_rhs, double* d_step, void* stream) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(d_step != nullptr && k >= 0 && k < h->ld / LU_NB, LLS_ERR_ARG, "lls_dist_lu_owner: bad arguments");
+    PhaseTimer t(h, (cudaStream_t)stream, 2);
+    return lu_dist_owner(h, k, with_rhs ? wf(h, W_RHS) : nullptr, d_step, (cudaStream_t)stream);
+}
+
+extern "C" int lls_dist_lu_update(lls_scene* h, int k, int with_rhs, const double* d_step, void* stream) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(d_step != nullptr && k >= 0 && k < h->ld / LU_NB, LLS_ERR_ARG, "lls_dist_lu_update: bad arguments");
+    PhaseTimer t(h, (cudaStream_t)stream, 2);
+    return lu_dist_update(h, k, with_rhs ? wf(h, W_RHS) : nullptr, d_step, (cudaStream_t)stream);
+}
+
+extern "C" int lls_dist_back(lls_scene* h, int k, void* stream) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(k >= 0 && k < h->ld / LU_NB, LLS_ERR_ARG, "lls_dist_back: bad arguments");
+    PhaseTimer t(h, (cudaStream_t)stream, 3);
+    return lu_dist_back(h, k, wf(h, W_RHS), wf(h, W_X), (cudaStream_t)stream);
 }
 
 extern "C" int lls_get_status(lls_scene* h, void* stream, int* status) {

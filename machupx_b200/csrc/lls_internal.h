@@ -66,7 +66,16 @@ struct CaseStrides {
     size_t out = 0, V = 0, M = 0, ac = 0, seg = 0;   // doubles
     size_t work = 0;                                  // BYTES between the work regions of consecutive cases
     const int* active = nullptr;
+    // row partition of ONE large scene over the GPUs of a box: 64-row blocks dealt round-robin, rank r owns global blocks
+    // r, r + P, r + 2P ... stored consecutively (local block lb <-> global block lb * P + rank).  P = 1: everything local.
+    int P = 1, rank = 0;
 };
+__host__ __device__ __forceinline__ int global_row(const CaseStrides& cs, int local_row) {
+    return ((local_row >> 6) * cs.P + cs.rank) * 64 + (local_row & 63);
+}
+__host__ __device__ __forceinline__ bool owns_row(const CaseStrides& cs, int global_row_index) {
+    return ((global_row_index >> 6) % cs.P) == cs.rank;
+}
 template <class T>
 __device__ __forceinline__ T* case_ptr(T* p, size_t stride) { return p + (size_t)blockIdx.z * stride; }
 template <class T>
@@ -78,6 +87,7 @@ __device__ __forceinline__ T* case_work_ptr(T* p, size_t stride_bytes) {
 struct Scene {
     int n = 0, ld = 0, n_ac = 0, n_seg = 0, n_af = 0, flags = 0;
     int ncases = 1;             // > 1 after lls_bind_batch
+    int n_loc_blocks = 0;       // 64-row blocks of V / M stored on this rank (all of them unless lls_set_partition was called)
     CaseStrides cs;             // strides of the bound batch (active == nullptr)
     int* ctl = nullptr;         // batch control block (device): active[ncases], iterations[ncases], n_active
     int* h_ctl = nullptr;       // pinned host mirror of n_active
@@ -125,6 +135,12 @@ int launch_integrate(Scene* s, double* d_seg_fm, cudaStream_t st);
 int launch_scale_gamma_pro(Scene* s, cudaStream_t st);
 int lu_factor_solve(Scene* s, double* d_mat, double* d_rhs, double* d_x, cudaStream_t st, bool masked = false);  // rhs may be null
 int lu_solve_only(Scene* s, const double* d_mat, double* d_rhs_inout, cudaStream_t st);
+// row-partitioned LU, one block step at a time (the host owns the broadcasts between the steps)
+size_t lu_dist_step_doubles(const Scene* s, int k);
+int lu_dist_begin(Scene* s);
+int lu_dist_owner(Scene* s, int k, double* rhs, double* send, cudaStream_t st);
+int lu_dist_update(Scene* s, int k, double* rhs, const double* recv, cudaStream_t st);
+int lu_dist_back(Scene* s, int k, const double* y, double* x, cudaStream_t st);
 
 }  // namespace lls
 

@@ -570,6 +570,241 @@ __global__ void __launch_bounds__(NB) lu_forwardsolve_kernel(const double* __res
     }
 }
 
+// =====================================================================================================================
+// Row-partitioned LU for one large scene over the GPUs of a box.  Block rows are dealt
+// round-robin (owner of block row k = k mod P), so the trailing update stays balanced.  Per block step k:
+//   owner(k):  lu_dist_owner_kernel  - factors the (already updated) diagonal tile, solves the U block row
+//                                      U[k, k+1:] = L11^-1 A[k, k+1:], y_k = L11^-1 b_k, and packs
+//                                      [diag image | y_k | U tiles] into one contiguous send buffer
+//   host:      NCCL broadcast of that buffer (torch.distributed), root = owner(k)
+//   all ranks: lu_dist_panel_kernel  - L[i,k] = A[i,k] U11^-1 and b_i -= L[i,k] y_k for the local block rows i > k
+//              lu_dist_update_kernel - A[i,j] -= L[i,k] U[k,j] for the local block rows i > k, all j > k (DMMA)
+// Back substitution walks the block rows backwards; the owner of block row k forms x_k from its row of U and the replicated
+// x_{>k} (lu_dist_back_kernel) and the 64 new values are broadcast.
+// =====================================================================================================================
+constexpr int DIST_HDR = PUB_DOUBLES + NB;      // doubles before the packed U tiles in the step buffer
+
+__global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_owner_kernel(double* __restrict__ Mloc, int ld, int k, int lbk, int ncols,
+                                                                      double* __restrict__ rhs, double* __restrict__ send,
+                                                                      double* __restrict__ uinv, int* __restrict__ flags, int epoch,
+                                                                      double* __restrict__ scalars, int* __restrict__ status) {
+    extern __shared__ __align__(16) double sm[];
+    double* sA = sm;
+    double* sC = sm + NB * TS;
+    __shared__ __align__(16) PivotLine pl;
+    __shared__ __align__(16) double dinv[NB];
+    const int t = threadIdx.x, b = blockIdx.x;
+    const bool diag = (b == 0);
+    double* gC = Mloc + (size_t)lbk * NB * ld + (size_t)(k + b) * NB;     // tile (k, k + b)
+    constexpr int IMG2 = NB * TS / 2;
+    load_tile_async(sC, gC, ld);
+    async_wait_all();
+    __syncthreads();
+    if (diag) {
+        factor_block(sC, pl);
+        if (t < NB) dinv[t] = 1.0 / sC[t * TS + t];
+        __syncthreads();
+        for (int e = t; e < NB * NB; e += LU_THREADS) {
+            const int r = e >> 6, c = e & 63;
+            const double v = sC[r * TS + c];
+            sA[r * TS + c] = (c > r) ? v * dinv[r] : v;
+        }
+        __syncthreads();
+        {
+            double2* g0 = reinterpret_cast<double2*>(send);
+            const double2* s0 = reinterpret_cast<const double2*>(sA);
+#pragma unroll
+            for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
+            if (t < NB) send[NB * TS + t] = dinv[t];
+        }
+        __threadfence();
+        __syncthreads();
+        if (t == 0) st_release(flags + k, epoch);
+        store_tile(gC, ld, sC);
+        if (t < NB) {
+            const double d = fabs(sC[t * TS + t]);
+            double m = d;
+            bool bad = !(d > 0.0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            bad = __any_sync(0xffffffffu, bad);
+            if ((t & 31) == 0) {
+                if (bad) atomicOr(status, LLS_STATUS_NAN);
+                pl.piv[t >> 5] = m;
+            }
+        }
+        __syncthreads();
+        if (t == 0) {
+            const double m = fmin(pl.piv[0], pl.piv[1]);
+            scalars[1] = (k == 0) ? m : fmin(m, scalars[1]);
+        }
+        if (rhs != nullptr && t < 32) {
+            forward_rhs_warp(sC, rhs + (size_t)k * NB);
+            __syncwarp();
+            send[PUB_DOUBLES + t] = rhs[(size_t)k * NB + t];
+            send[PUB_DOUBLES + 32 + t] = rhs[(size_t)k * NB + 32 + t];
+        }
+    } else {
+        if (t == 0) {
+            while (ld_acquire(flags + k) != epoch) __nanosleep(32);
+        }
+        __syncthreads();
+        const double2* g = reinterpret_cast<const double2*>(send);
+        double2* sT2 = reinterpret_cast<double2*>(sA);
+        double2 v[IMG2 / LU_THREADS];
+#pragma unroll
+        for (int u = 0; u < IMG2 / LU_THREADS; ++u) v[u] = __ldcg(g + t + u * LU_THREADS);
+#pragma unroll
+        for (int u = 0; u < IMG2 / LU_THREADS; ++u) sT2[t + u * LU_THREADS] = v[u];
+        if (t < NB) dinv[t] = 1.0;
+        __syncthreads();
+    }
+    {
+        const int ty = t >> 3, tx = t & 7;
+        const int sr = diag ? TS : 1, sc = diag ? 1 : TS;
+        double a[4][8];
+        if (diag) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = (ty + 16 * i == tx + 8 * j) ? 1.0 : 0.0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc];
+        }
+        if (diag) panel_solve<false>(a, sA, dinv);
+        else panel_solve<true>(a, sA, dinv);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
+    }
+    __syncthreads();
+    if (diag) {
+        store_tile(uinv + (size_t)k * NB * NB, NB, sC);
+    } else {
+        store_tile(gC, ld, sC);
+        store_tile(send + DIST_HDR + (size_t)(b - 1) * NB * NB, NB, sC);      // packed copy for the broadcast
+    }
+    (void)ncols;
+}
+
+// L[i,k] = A[i,k] U11^-1 and b_i -= L[i,k] y_k for the local block rows lb >= lb0 (their global index is > k)
+__global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_panel_kernel(double* __restrict__ Mloc, int ld, int k, int lb0, int P, int rank,
+                                                                      const double* __restrict__ recv, double* __restrict__ rhs) {
+    extern __shared__ __align__(16) double sm[];
+    double* sA = sm;
+    double* sC = sm + NB * TS;
+    __shared__ __align__(16) double dinv[NB];
+    __shared__ double yk[NB];
+    const int t = threadIdx.x;
+    const int lb = lb0 + blockIdx.x;
+    double* gC = Mloc + (size_t)lb * NB * ld + (size_t)k * NB;
+    constexpr int IMG2 = NB * TS / 2;
+    load_tile_async(sC, gC, ld);
+    {
+        const double2* g = reinterpret_cast<const double2*>(recv);
+        double2* sT2 = reinterpret_cast<double2*>(sA);
+#pragma unroll
+        for (int u = 0; u < IMG2 / LU_THREADS; ++u) sT2[t + u * LU_THREADS] = g[t + u * LU_THREADS];
+        if (t < NB) {
+            dinv[t] = recv[NB * TS + t];
+            yk[t] = recv[PUB_DOUBLES + t];
+        }
+    }
+    async_wait_all();
+    __syncthreads();
+    {
+        const int ty = t >> 3, tx = t & 7;
+        double a[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * TS + tx + 8 * j];
+        panel_solve<false>(a, sA, dinv);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * TS + tx + 8 * j] = a[i][j];
+    }
+    __syncthreads();
+    store_tile(gC, ld, sC);
+    if (rhs != nullptr && t < NB) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int q = 0; q < NB; ++q) s = fma(sC[t * TS + q], yk[q], s);
+        rhs[(size_t)(lb * P + rank) * NB + t] -= s;
+    }
+}
+
+// A[i,j] -= L[i,k] U[k,j] for the local block rows lb >= lb0 and all block columns j > k (U tiles from the step buffer)
+__global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_update_kernel(double* __restrict__ Mloc, int ld, int k, int lb0, int ncols,
+                                                                       const double* __restrict__ utiles) {
+    extern __shared__ __align__(16) double sm[];
+    double* sA = sm;
+    double* sB = sm + NB * TS;
+    const int lb = lb0 + blockIdx.x / ncols;
+    const int jj = blockIdx.x % ncols;                 // block column k + 1 + jj
+    double* gC = Mloc + (size_t)lb * NB * ld + (size_t)(k + 1 + jj) * NB;
+    double acc[4][4][2];
+    load_tile_async(sA, Mloc + (size_t)lb * NB * ld + (size_t)k * NB, ld);
+    load_tile_async(sB, utiles + (size_t)jj * NB * NB, NB);
+    acc_io<true>(acc, gC, ld);
+    async_wait_all();
+    __syncthreads();
+    mma_tile(sA, sB, acc);
+    acc_io<false>(acc, gC, ld);
+}
+
+// x_k = inv(U_kk) (y_k - sum_{j>k} U[k,j] x_j) on the owner of block row k.  CTAs split the columns; partial sums meet in
+// `acc` (64 doubles + a ticket, zero on entry and left zero), the last CTA to arrive finishes the block.
+constexpr int BACK_CHUNK = 1024;
+__global__ void __launch_bounds__(256) lu_dist_back_kernel(const double* __restrict__ Mloc, int ld, int k, int lbk,
+                                                           const double* __restrict__ uinv, const double* __restrict__ y,
+                                                           double* __restrict__ x, double* __restrict__ acc) {
+    __shared__ double sv[NB];
+    __shared__ int last;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int c0 = (k + 1) * NB + blockIdx.x * BACK_CHUNK;
+    const int c1 = min(c0 + BACK_CHUNK, ld);
+    const double* rowbase = Mloc + (size_t)lbk * NB * ld;
+    if (c0 < c1) {
+#pragma unroll 1
+        for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+            const double* row = rowbase + (size_t)r * ld;
+            double s = 0.0;
+            for (int c = c0 + lane; c < c1; c += 32) s = fma(row[c], __ldcg(x + c), s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) atomicAdd(acc + r, s);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        int* ticket = reinterpret_cast<int*>(acc + NB);
+        last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (t < NB) sv[t] = y[(size_t)k * NB + t] - __ldcg(acc + t);
+    __syncthreads();
+    if (t < NB) {
+        const double* ui = uinv + (size_t)k * NB * NB + (size_t)t * NB;
+        double s = 0.0;
+#pragma unroll 8
+        for (int q = 0; q < NB; ++q) s = fma(ui[q], sv[q], s);
+        x[(size_t)k * NB + t] = s;
+        acc[t] = 0.0;
+    }
+    if (t == 0) *reinterpret_cast<int*>(acc + NB) = 0;
+}
+
 #ifdef LLS_LU_CLOCKS
 extern "C" int lls_debug_lu_clocks(long long* out16) {
     return cudaMemcpyFromSymbol(out16, g_lu_clocks, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
@@ -626,6 +861,65 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
         lu_backsolve_chain_kernel<<<dim3(nblk, 1, ncases), BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, rhs, x, s->lu_flags + nblk + 1, epoch, cs);
         count_launch();
     }
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+// ---- host side of the row-partitioned LU (driven step by step from Python, which owns the NCCL broadcasts) -------------
+size_t lu_dist_step_doubles(const Scene* s, int k) {
+    const int nblk = s->ld / NB;
+    return (size_t)DIST_HDR + (size_t)(nblk - 1 - k) * NB * NB;
+}
+
+int lu_dist_begin(Scene* s) {
+    LLS_TRY(lu_prepare(s));
+    static bool attr = false;
+    if (!attr) {
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        attr = true;
+    }
+    ++s->lu_epoch;
+    return LLS_OK;
+}
+
+int lu_dist_owner(Scene* s, int k, double* rhs, double* send, cudaStream_t st) {
+    const int nblk = s->ld / NB, P = s->cs.P;
+    LLS_REQUIRE(k % P == s->cs.rank, LLS_ERR_ARG, "lu_dist_owner: this rank does not own block row k");
+    const int ncols = nblk - 1 - k;
+    lu_dist_owner_kernel<<<1 + ncols, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, k / P, ncols, rhs, send, s->uinv, s->lu_flags, s->lu_epoch,
+                                                                        s->scalars, s->status);
+    count_launch();
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+int lu_dist_update(Scene* s, int k, double* rhs, const double* recv, cudaStream_t st) {
+    const int nblk = s->ld / NB, P = s->cs.P, rank = s->cs.rank;
+    const int ncols = nblk - 1 - k;
+    // first local block whose global index lb * P + rank exceeds k
+    int lb0 = (k + 1 - rank + P - 1) / P;
+    if (lb0 < 0) lb0 = 0;
+    const int nloc = s->n_loc_blocks - lb0;
+    if (nloc <= 0) return LLS_OK;
+    lu_dist_panel_kernel<<<nloc, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, lb0, P, rank, recv, rhs);
+    count_launch();
+    if (ncols > 0) {
+        lu_dist_update_kernel<<<nloc * ncols, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, lb0, ncols, recv + DIST_HDR);
+        count_launch();
+    }
+    LLS_CUDA_TRY(cudaGetLastError());
+    return LLS_OK;
+}
+
+int lu_dist_back(Scene* s, int k, const double* y, double* x, cudaStream_t st) {
+    const int P = s->cs.P;
+    LLS_REQUIRE(k % P == s->cs.rank, LLS_ERR_ARG, "lu_dist_back: this rank does not own block row k");
+    const int cols = s->ld - (k + 1) * NB;
+    const int grid = cols > 0 ? (cols + BACK_CHUNK - 1) / BACK_CHUNK : 1;
+    lu_dist_back_kernel<<<grid, 256, 0, st>>>(s->M, s->ld, k, k / P, s->uinv, y, x, s->inv + 2 * PUB_DOUBLES);
+    count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }
