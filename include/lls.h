@@ -208,7 +208,7 @@ int lls_dist_assemble(lls_scene* h, int newton, void* stream);
 int lls_dist_residual(lls_scene* h, void* stream, double* local_sum);
 int lls_dist_update_gamma(lls_scene* h, double relaxation, void* stream);
 int lls_dist_vectors(lls_scene* h, double** d_rhs, double** d_x, double** d_gamma);
-int lls_dist_lu_begin(lls_scene* h, size_t* max_step_doubles);
+int lls_dist_lu_begin(lls_scene* h, size_t* max_step_doubles, void* stream);
 int lls_dist_lu_step_doubles(lls_scene* h, int k, size_t* doubles);
 int lls_dist_lu_owner(lls_scene* h, int k, int with_rhs, double* d_step, void* stream);
 int lls_dist_lu_update(lls_scene* h, int k, int with_rhs, const double* d_step, void* stream);

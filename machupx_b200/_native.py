@@ -38,7 +38,7 @@ SIGNATURES = {
     "lls_dist_residual": (_i, [_vp, _vp, _pd]),
     "lls_dist_update_gamma": (_i, [_vp, _d, _vp]),
     "lls_dist_vectors": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
-    "lls_dist_lu_begin": (_i, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
+    "lls_dist_lu_begin": (_i, [_vp, ctypes.POINTER(ctypes.c_size_t), _vp]),
     "lls_dist_lu_step_doubles": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_size_t)]),
     "lls_dist_lu_owner": (_i, [_vp, _i, _i, _vp, _vp]),
     "lls_dist_lu_update": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -379,11 +379,11 @@ extern "C" int lls_dist_vectors(lls_scene* h, double** d_rhs, double** d_x, doub
     return LLS_OK;
 }
 
-extern "C" int lls_dist_lu_begin(lls_scene* h, size_t* max_step_doubles) {
+extern "C" int lls_dist_lu_begin(lls_scene* h, size_t* max_step_doubles, void* stream) {
     LLS_CHECK_BOUND(h);
     LLS_CHECK_PART(h);
     if (max_step_doubles) *max_step_doubles = lu_dist_step_doubles(h, 0);
-    return lu_dist_begin(h);
+    return lu_dist_begin(h, (cudaStream_t)stream);
 }
 
 extern "C" int lls_dist_lu_step_doubles(lls_scene* h, int k, size_t* doubles) {

@@ -137,7 +137,7 @@ int lu_factor_solve(Scene* s, double* d_mat, double* d_rhs, double* d_x, cudaStr
 int lu_solve_only(Scene* s, const double* d_mat, double* d_rhs_inout, cudaStream_t st);
 // row-partitioned LU, one block step at a time (the host owns the broadcasts between the steps)
 size_t lu_dist_step_doubles(const Scene* s, int k);
-int lu_dist_begin(Scene* s);
+int lu_dist_begin(Scene* s, cudaStream_t st);
 int lu_dist_owner(Scene* s, int k, double* rhs, double* send, cudaStream_t st);
 int lu_dist_update(Scene* s, int k, double* rhs, const double* recv, cudaStream_t st);
 int lu_dist_back(Scene* s, int k, const double* y, double* x, cudaStream_t st);

@@ -871,7 +871,7 @@ size_t lu_dist_step_doubles(const Scene* s, int k) {
     return (size_t)DIST_HDR + (size_t)(nblk - 1 - k) * NB * NB;
 }
 
-int lu_dist_begin(Scene* s) {
+int lu_dist_begin(Scene* s, cudaStream_t st) {
     LLS_TRY(lu_prepare(s));
     static bool attr = false;
     if (!attr) {
@@ -880,7 +880,10 @@ int lu_dist_begin(Scene* s) {
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         attr = true;
     }
-    ++s->lu_epoch;
+    // the publish flags are cleared in stream order instead of relying on a fresh epoch, so that a whole factorisation
+    // (kernels + NCCL broadcasts) can be captured once into a CUDA graph and replayed with the same arguments
+    LLS_CUDA_TRY(cudaMemsetAsync(s->lu_flags, 0, sizeof(int) * (size_t)(s->ld / NB + 1), st));
+    if (s->lu_epoch == 0) s->lu_epoch = 1;
     return LLS_OK;
 }
 

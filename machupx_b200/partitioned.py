@@ -17,6 +17,7 @@ the collectives are issued here through ``torch.distributed`` (NCCL over NVLink 
 drive exactly the same control flow with a numpy implementation of the local work (tests/test_partitioned_cpu.py).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -191,7 +192,7 @@ class PartitionedDeviceScene:
                                             p(self.d_work), ctypes.c_size_t(int(sizes.work_bytes))))
             _native.check(self.lib.lls_set_state(self.handle, p(self.d_ac)))
             step = ctypes.c_size_t(0)
-            _native.check(self.lib.lls_dist_lu_begin(self.handle, ctypes.byref(step)))
+            _native.check(self.lib.lls_dist_lu_begin(self.handle, ctypes.byref(step), self._st()))
             self.d_step = torch.zeros(int(step.value), dtype=torch.float64, device=dev)
             rhs, x, gam = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
             _native.check(self.lib.lls_dist_vectors(self.handle, ctypes.byref(rhs), ctypes.byref(x), ctypes.byref(gam)))
@@ -200,6 +201,32 @@ class PartitionedDeviceScene:
         self.impingement_threshold = 1e-10
         self.comm = TorchComm(group, dev) if dist.is_initialized() else LocalComm()
         self.solver = PartitionedSolver(self, self.comm, self.nblk, self.world, self.rank)
+        # One factorisation + back substitution = 3 launches and 1-2 broadcasts per block step, thousands of tiny host calls:
+        # after a warm-up pass it is captured into a CUDA graph (NCCL broadcasts included) and replayed.
+        self.use_graph = os.environ.get("LLS_PARTITIONED_GRAPH", "0") == "1"   # off by default: capture with NCCL hung on the 2-GPU box (round 1)
+        self._lu_graph = None
+        self._lu_calls = 0
+        plain = self.solver.lu_solve
+
+        def lu_solve_graphed():
+            self._lu_calls += 1
+            if not self.use_graph or self._lu_calls == 1:
+                return plain()                      # first pass warms NCCL and the kernels up
+            if self._lu_graph is None:
+                try:
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        plain()
+                    self._lu_graph = g
+                except Exception as exc:            # capture not possible in this environment: keep the plain loop
+                    self.use_graph = False
+                    self.graph_error = repr(exc)
+                    torch.cuda.synchronize(self.device)
+                    return plain()
+            self._lu_graph.replay()
+
+        self.solver.lu_solve = lu_solve_graphed
 
     def __del__(self):
         try:
@@ -236,7 +263,7 @@ class PartitionedDeviceScene:
         self._call(self.lib.lls_dist_update_gamma, float(relaxation), self._st())
 
     def lu_begin(self):
-        self._call(self.lib.lls_dist_lu_begin, None)
+        self._call(self.lib.lls_dist_lu_begin, None, self._st())
 
     def step_buffer(self, k):
         nd = ctypes.c_size_t(0)
