@@ -41,7 +41,7 @@ else:
         for c in range(side):
             ac = copy.deepcopy(drone)
             eps = float(rng.uniform(-0.5, 0.5))
-            ac["state"]["position"] = [-10.0 * r, 10.0 * (c - (side - 1) / 2.0), -50.0 - 5.0 * ((r + c) % 2) + eps, "ft"]
+            ac["state"]["position"] = [-10.0 * r, 10.0 * (c - (side - 1) / 2.0), -50.0 - 5.0 * ((r + c) % 2) + eps]
             inp["scene"]["aircraft"]["drone_%d_%d" % (r, c)] = ac
 t0 = time.perf_counter(); scene = Scene(inp); t_host = time.perf_counter() - t0
 dev = PartitionedDeviceScene(scene._tables)
@@ -55,9 +55,11 @@ if os.environ.get("LLS_TIMING"):
     import ctypes
     from machupx_b200 import _native
     _native.check(dev.lib.lls_set_timing(dev.handle, 1))
-t0 = time.perf_counter()
-seg, it, err, status, hist = dev.solve(*args)
-torch.cuda.synchronize(); t_solve = time.perf_counter() - t0
+t_solve = None
+if not os.environ.get("SWARM_ONE_SOLVE"):
+    t0 = time.perf_counter()
+    seg, it, err, status, hist = dev.solve(*args)
+    torch.cuda.synchronize(); t_solve = time.perf_counter() - t0
 if os.environ.get("LLS_TIMING"):
     ms = (ctypes.c_double * 6)(); _native.check(dev.lib.lls_get_timings(dev.handle, ms))
     tm = dict(zip(("influence", "assemble", "lu", "trisolve", "residual", "integrate"), list(ms)))
