@@ -291,9 +291,9 @@ class Scene:
         spec = _LAZY_OUT.get(name)
         if spec is None:
             raise AttributeError(name)
-        if self.__dict__.get("_device") is None:
-            raise AttributeError("{0} is only available after solve_forces()".format(name))
         if self._out_cache is None:
+            if self.__dict__.get("_device") is None:
+                raise AttributeError("{0} is only available after solve_forces()".format(name))
             self._out_cache = self._device.out()
         f, width = spec
         return self._out_cache[f] if width == 1 else np.ascontiguousarray(self._out_cache[f:f + width].T)
@@ -309,6 +309,8 @@ class Scene:
         non_dimensional, dimensional, report_by_segment, body_frame, stab_frame, wind_frame, initial_guess, verbose."""
         if self._num_aircraft == 0:
             raise RuntimeError("There are no aircraft in this scene. No calculations can be performed.")
+        if kwargs.get("partitioned", False):
+            return self._solve_forces_partitioned(**kwargs)
         initial_guess = kwargs.get("initial_guess", "linear")
         verbose = kwargs.get("verbose", False)
         self._FM = {}
@@ -370,6 +372,50 @@ class Scene:
             if total > 0.0:
                 print("Solution rate: {0} Hz".format(1 / total))
 
+        filename = kwargs.get("filename", None)
+        if filename is not None:
+            with open(filename, "w") as handle:
+                json.dump(self._FM, handle, indent=4)
+        self._solved = True
+        return self._FM
+
+    def _solve_forces_partitioned(self, **kwargs):
+        """``solve_forces(partitioned=True)``: the rows of V_ji / A / J are dealt over the ranks of the default
+        ``torch.distributed`` group (one process per GPU, NCCL), so scenes the reference cannot hold
+        at all (N >= ~9k) and that exceed one GPU (N > ~72k) still solve.  Every rank must call it with the same scene;
+        every rank gets the same ``FM``.  ``_gamma`` is replicated; the other per-point arrays are only filled for the rows a
+        rank owns."""
+        from .partitioned import PartitionedDeviceScene
+        if self._current_pose_key() != self._pose_key:
+            self._perform_geometry_and_atmos_calcs()
+        elif self._current_controls_key() != self._controls_key:
+            for f, values in flap_rows(self).items():
+                self._tables["tab"][f, :self._N] = values
+            self._controls_key = self._current_controls_key()
+            self._part_tables_id = None
+        dev = getattr(self, "_part_device", None)
+        if dev is None or getattr(self, "_part_tables_id", None) != id(self._tables):
+            dev = self._part_device = PartitionedDeviceScene(self._tables)
+            self._part_tables_id = id(self._tables)
+        dev.upload_state(build_aircraft_state(self))
+        self._FM = {}
+        self._out_cache = None
+        seg, its, err, status, hist = dev.solve(self._solver_type, self._solver_convergence, self._solver_relaxation,
+                                                self._max_solver_iterations, self._impingement_threshold)
+        self._last_iterations, self._last_error, self._error_history, self._seg_fm = its, err, hist, seg
+        self._device = None
+        self._out_cache = dev.d_out[:, :self._N].cpu().numpy()
+        try:
+            if status & L.STATUS_IMPINGEMENT:
+                warnings.warn(_IMPINGEMENT_TEXT)
+            if status & L.STATUS_NOT_CONVERGED:
+                raise SolverNotConvergedError(self._solver_type, err)
+        except Exception as e:
+            self._handle_error(e)
+        body, stab, wind = self._get_frames(**kwargs)
+        self._FM = assemble_fm(seg, self._frames(), non_dimensional=kwargs.get("non_dimensional", True),
+                               dimensional=kwargs.get("dimensional", True), report_by_segment=kwargs.get("report_by_segment", False),
+                               body_frame=body, stab_frame=stab, wind_frame=wind)
         filename = kwargs.get("filename", None)
         if filename is not None:
             with open(filename, "w") as handle:

@@ -40,3 +40,21 @@ def test_partitioned_two_gpus_nccl():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     rows = _parse(out.stdout)
     assert all(r["world"] == 2 for r in rows)
+
+
+def test_scene_api_partitioned_equals_regular():
+    import copy
+    import numpy as np
+    from machupx_b200 import Scene
+    with open(os.path.join(ROOT, "tests", "golden", "swarm_nonlinear.json")) as fh:
+        inp = json.load(fh)["input"]
+    scene = Scene(copy.deepcopy(inp))
+    FM_a = scene.solve_forces()
+    gamma_a = np.array(scene._gamma)
+    FM_b = scene.solve_forces(partitioned=True)
+    assert np.abs(np.asarray(scene._gamma) - gamma_a).max() <= 1e-12 * np.abs(gamma_a).max()
+    for name in FM_a:
+        for key, val in FM_a[name]["total"].items():
+            assert abs(FM_b[name]["total"][key] - val) <= 1e-11 * max(1.0, abs(val)), (name, key)
+    FM_c = scene.solve_forces()          # and back to the single-GPU path
+    assert abs(FM_c["drone0"]["total"]["CL"] - FM_a["drone0"]["total"]["CL"]) < 1e-13
