@@ -40,6 +40,7 @@ extern "C" {
 #define LLS_STATUS_IMPINGEMENT 2
 #define LLS_STATUS_NAN 4
 #define LLS_STATUS_SMALL_PIVOT 8
+#define LLS_STATUS_SECTION_BOUNDS 16 /* a poly_fit airfoil was evaluated outside the limits of its fit (airfoil_db: PolyFitBoundsError) */
 
 /* ---- solver flags (reference: scene.py:82-87) ------------------------------------------ */
 #define LLS_FLAG_SWEPT_SECTIONS 1
@@ -108,8 +109,16 @@ enum lls_airfoil_field {
     LLS_AF_CD1 = 6,
     LLS_AF_CD2 = 7,
     LLS_AF_CLMAX = 8,
+    /* poly_fit airfoils (LLS_AF_TYPE == 1) reuse the block: */
+    LLS_AF_POLY_OFF = 1,  /* offset (in doubles, from the start of the airfoil buffer) of this airfoil's record in the pool      */
+    LLS_AF_POLY_NDOF = 2, /* number of independent variables V (<= 5)                                                       */
+    LLS_AF_POLY_DOF0 = 3, /* V kind codes: 0 alpha, 1 Rey, 2 Mach, 3 trailing_flap_deflection [rad], 4 trailing_flap_fraction */
     LLS_AF_STRIDE = 16
 };
+/* Pool record of a poly_fit airfoil (doubles), after the n_airfoils parameter blocks of the airfoil buffer:
+ *   limits: V x (lower, upper); then for CL, CD, Cm in this order: ncoef, V degrees, ncoef coefficients
+ * with the coefficient index running like airfoil_db's fits: exponent tuple row-major, LAST variable fastest
+ * (reference machupX/poly_fits.py:398-431 compose_j). */
 
 /* ---- per-aircraft state block, doubles --------------------------------------------------- */
 enum lls_aircraft_field {

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int fl
                                                            const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                            const double* __restrict__ V, double* __restrict__ W,
                                                            double* __restrict__ out, double* __restrict__ partial, int vel_only,
-                                                           CaseStrides cs) {
+                                                           int* __restrict__ status, CaseStrides cs) {
     if (LLS_CASE_INACTIVE(cs)) return;
     V = case_ptr(V, cs.V);
     W = case_work_ptr(W, cs.work);
@@ -170,9 +170,11 @@ __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int fl
     const double va = dot(vi, ua), vn = dot(vi, un);                              // scene.py:751-753
     const double alpha = atan2(vn, va);
     const SectionParams sp = load_section(tab, itab, af, ld, i);
-    const double CLa = section_CLa(sp);                                           // scene.py:765-768
-    double CL = section_CL(sp, alpha);
+    bool oob = false;
+    const double CLa = section_CLa(sp, alpha, Re, Mach);                          // scene.py:765-768
+    double CL = section_CL(sp, alpha, Re, Mach, oob);
     const double CLRe = section_CLRe(sp, alpha, Re, Mach), CLM = section_CLM(sp, alpha, Re, Mach);
+    if (oob) atomicOr(case_work_ptr(status, cs.work), LLS_STATUS_SECTION_BOUNDS);
     const double dS = tab[(size_t)LLS_F_DS * ld + i];
     const double Vinf = W[(size_t)W_VINF_MAG * ld + i];
     const double Vfix = in_plane ? W[(size_t)W_VINF_IP * ld + i] : Vinf;
@@ -257,7 +259,7 @@ int launch_assemble_linear(Scene* s, cudaStream_t st) {
 
 int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked) {
     residual_kernel<128><<<dim3(s->cs.P == 1 ? s->n : s->n_loc_blocks * 64, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
-                                                                  vel_only, strides(s, masked));
+                                                                  vel_only, s->status, strides(s, masked));
     count_launch();
     if (!vel_only) {
         sum_kernel<<<dim3(1, 1, s->ncases), 256, 0, st>>>(s->n, s->partial, s->scalars, 0, strides(s, masked));

@@ -49,17 +49,25 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
         st3(out, ld, LLS_O_UTRAIL1, i, Vec3{j1.x / m1, j1.y / m1, j1.z / m1});
     }
     const Vec3 us = ld3(tab, ld, LLS_F_US, i), ua = ld3(tab, ld, LLS_F_UA, i), un = ld3(tab, ld, LLS_F_UN, i);
-    double vinf_ip = vinf_mag;
+    double vinf_ip = vinf_mag, vir_ip = vir_mag;
     if (flags & LLS_FLAG_IN_PLANE) {                                             // scene.py:637-641
-        Vec3 p = vinf - dot(us, vinf) * us;
+        const Vec3 p = vinf - dot(us, vinf) * us;
         vinf_ip = norm(p);
+        const Vec3 pr = vir - dot(us, vir) * us;
+        vir_ip = norm(pr);
     }
     W[(size_t)W_VINF_IP * ld + i] = vinf_ip;
+    // Reynolds and Mach number of the linear pre-pass (scene.py:642-646; the in-plane branch really mixes the two speeds)
+    const double cbar = tab[(size_t)LLS_F_CBAR * ld + i];
+    const double Re = ((flags & LLS_FLAG_IN_PLANE) ? vir_ip : vinf_mag) * cbar / tab[(size_t)LLS_F_NU * ld + i];
+    const double Mach = ((flags & LLS_FLAG_IN_PLANE) ? vinf_ip : vinf_mag) / tab[(size_t)LLS_F_SOS * ld + i];
     const double alpha_inf = atan2(dot(vir, un), dot(vir, ua));                  // scene.py:649-651
     SectionParams sp = load_section(tab, itab, af, ld, i);
-    const double CLa = section_CLa(sp);                                          // scene.py:659-661
-    double CL = section_CL(sp, alpha_inf);
-    const double aL0 = section_aL0(sp);
+    bool oob = false;
+    const double CLa = section_CLa(sp, alpha_inf, Re, Mach);                     // scene.py:659-661
+    double CL = section_CL(sp, alpha_inf, Re, Mach, oob);
+    const double aL0 = section_aL0(sp, Re, Mach);
+    if (oob) atomicOr(status, LLS_STATUS_SECTION_BOUNDS);
     if (flags & LLS_FLAG_SWEPT_SECTIONS) {                                       // scene.py:665-666, 797
         CL += CLa * (aL0 - aL0 * tab[(size_t)LLS_F_CSWI * ld + i]);
     }

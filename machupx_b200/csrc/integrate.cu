@@ -32,7 +32,8 @@ constexpr int INT_THREADS = 128;
 __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                                 const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                                 const double* __restrict__ W, double* __restrict__ out,
-                                                                double* __restrict__ seg_fm, CaseStrides cs) {
+                                                                double* __restrict__ seg_fm, int* __restrict__ status, CaseStrides cs) {
+    status = case_work_ptr(status, cs.work);
     W = case_work_ptr(W, cs.work);
     out = case_ptr(out, cs.out);
     seg_fm = case_ptr(seg_fm, cs.seg);
@@ -69,7 +70,6 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
             Re_unswept = Vi * cbar / nu;
             alpha_unswept = alpha;
         }
-        (void)Re_unswept;  // linear airfoils carry no Reynolds dependence
         const double Vsec = in_plane ? sqrt(Vip2) : Vi;                              // scene.py:975-981
         const double Re = Vsec * cbar / nu, Mach = Vsec / sos;
         double redim_full, redim_ip;
@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
             redim_ip = 0.5 * rho * Vinf_ip * Vinf_ip * dS;
         }
         const SectionParams sp = load_section(tab, itab, af, ld, i);
-        const double CD = section_CD(sp, alpha_unswept);                             // scene.py:1014-1017
-        double Cm = section_Cm(sp, alpha);                                           // scene.py:1020
+        bool oob = false;
+        const double CD = section_CD(sp, alpha_unswept, Re_unswept, Mach, oob);      // scene.py:1014-1017
+        double Cm = section_Cm(sp, alpha, Re, Mach, oob);                            // scene.py:1020
+        if (oob) atomicOr(status, LLS_STATUS_SECTION_BOUNDS);
         if (swept) Cm *= cswi;                                                       // scene.py:1026
         const Vec3 dM_section = ((in_plane ? redim_ip : redim_full) * cbar * Cm) * us;   // scene.py:1029-1032
         const Vec3 dM_inv = cross(rcg, dF_inv) + dM_section;                         // scene.py:1035-1036
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
 
 int launch_integrate(Scene* s, double* d_seg_fm, cudaStream_t st) {
     integrate_kernel<<<dim3(s->n_seg, 1, s->ncases), INT_THREADS, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out, d_seg_fm,
-                                                                           strides(s, false));
+                                                                           s->status, strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;

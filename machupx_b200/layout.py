@@ -18,7 +18,9 @@ NI = 7
 
 # airfoil block (enum lls_airfoil_field)
 AF_TYPE, AF_AL0, AF_CLA, AF_CML0, AF_CMA, AF_CD0, AF_CD1, AF_CD2, AF_CLMAX = 0, 1, 2, 3, 4, 5, 6, 7, 8
+AF_POLY_OFF, AF_POLY_NDOF, AF_POLY_DOF0 = 1, 2, 3   # poly_fit airfoils (AF_TYPE == 1) reuse the block
 AF_STRIDE = 16
+POLY_DOF_KINDS = ("alpha", "Rey", "Mach", "trailing_flap_deflection", "trailing_flap_fraction")
 
 # per-aircraft state block (enum lls_aircraft_field)
 AC_VTRANS, AC_W, AC_POS, AC_CGR = 0, 3, 6, 9
@@ -35,7 +37,7 @@ FLAG_SWEPT_SECTIONS, FLAG_TOTAL_VELOCITY, FLAG_IN_PLANE, FLAG_MATCH_MACHUP_PRO =
 FLAG_DEFAULT = FLAG_SWEPT_SECTIONS | FLAG_TOTAL_VELOCITY | FLAG_IN_PLANE
 
 # status bits
-STATUS_NOT_CONVERGED, STATUS_IMPINGEMENT, STATUS_NAN, STATUS_SMALL_PIVOT = 1, 2, 4, 8
+STATUS_NOT_CONVERGED, STATUS_IMPINGEMENT, STATUS_NAN, STATUS_SMALL_PIVOT, STATUS_SECTION_BOUNDS = 1, 2, 4, 8, 16
 
 LD_ALIGN = 64  # leading dimension is N rounded up to this many elements
 

@@ -346,6 +346,8 @@ class Scene:
                 if verbose: print("Nonlinear solver successfully converged. Final error: {0}".format(err))
             elif dev.status() & L.STATUS_IMPINGEMENT:
                 warnings.warn(_IMPINGEMENT_TEXT)
+            if dev.status() & L.STATUS_SECTION_BOUNDS:
+                raise DatabaseBoundsError("A poly_fit airfoil was evaluated outside the limits of its fit.")
         except Exception as e:
             self._handle_error(e)
 

@@ -56,6 +56,7 @@ class Tables:
         self.RHO, self.NU, self.SOS = s1(L.F_RHO), s1(L.F_NU), s1(L.F_SOS)
         self.WB = s1(L.F_WB)
         self.FLAP_DA, self.FLAP_DCM, self.FLAP_DCD = s1(L.F_FLAP_DA), s1(L.F_FLAP_DCM), s1(L.F_FLAP_DCD)
+        self.FLAP_DEFL, self.FLAP_CF = s1(L.F_FLAP_DEFL), s1(L.F_FLAP_CF)
         self.wing_begin = itab[L.I_WING_BEGIN, :n].astype(np.int64)
         self.wing_end = itab[L.I_WING_END, :n].astype(np.int64)
         self.aircraft = itab[L.I_AIRCRAFT, :n].astype(np.int64)
@@ -191,34 +192,134 @@ def _blend(T, fa, fb):
     return (1.0 - T.WB) * fa + T.WB * fb
 
 
-def section_CL(T, alpha):
-    def one(ids):
+# poly_fit airfoils (airfoil_db "poly_fit" type; third party, semantics defined in machupx_b200/airfoil.py and
+# include/lls.h; PARITY UNPINNED by the reference).  Plain restatement: decompose the coefficient index into the exponent
+# tuple (last variable fastest, reference machupX/poly_fits.py:433-480) and sum the monomials.
+def _poly_record(T, a, which):
+    flat = T.af.ravel()
+    blk = T.af[a]
+    V = int(blk[L.AF_POLY_NDOF])
+    kinds = [int(blk[L.AF_POLY_DOF0 + v]) for v in range(V)]
+    off = int(blk[L.AF_POLY_OFF])
+    limits = flat[off:off + 2 * V].reshape(V, 2)
+    pos = off + 2 * V
+    for _ in range(which):
+        pos += 1 + V + int(flat[pos])
+    ncoef = int(flat[pos])
+    degrees = [int(x) for x in flat[pos + 1:pos + 1 + V]]
+    coefs = flat[pos + 1 + V:pos + 1 + V + ncoef]
+    return kinds, limits, degrees, coefs
+
+
+def _poly_one(T, a, mask, alpha, Re, M, which, dkind):
+    kinds, limits, degrees, coefs = _poly_record(T, a, which)
+    xs = []
+    for k in kinds:
+        xs.append({0: alpha, 1: Re, 2: M, 3: T.FLAP_DEFL, 4: T.FLAP_CF}[k][mask])
+    if dkind is not None and dkind not in kinds:
+        return np.zeros(mask.sum())
+    out = np.zeros(mask.sum())
+    for j, c in enumerate(coefs):
+        rest, exps = j, []
+        for d in reversed(degrees):
+            exps.append(rest % (d + 1))
+            rest //= (d + 1)
+        exps = exps[::-1]
+        term = np.full(mask.sum(), c)
+        for k, x, e in zip(kinds, xs, exps):
+            if dkind is not None and k == dkind:
+                term = term * (e * x ** (e - 1) if e > 0 else 0.0)
+            else:
+                term = term * x ** e
+        out += term
+    return out
+
+
+def _per_airfoil(T, ids, alpha, Re, M, linear_fn, which, dkind=None):
+    """Evaluates one bracketing airfoil per control point: linear_fn(ids) for linear airfoils, the polynomial otherwise."""
+    out = linear_fn(ids)
+    for a in np.unique(ids):
+        if T.af[a, L.AF_TYPE] > 0.5:
+            mask = ids == a
+            out = np.array(out, dtype=float)
+            out[mask] = _poly_one(T, a, mask, alpha, Re, M, which, dkind)
+    return out
+
+
+def _zeros(T):
+    return np.zeros(T.n)
+
+
+def section_CL(T, alpha, Re=None, M=None):
+    Re = _zeros(T) if Re is None else Re
+    M = _zeros(T) if M is None else M
+
+    def lin(ids):
         cl = _af(T, ids, L.AF_CLA) * (alpha - _af(T, ids, L.AF_AL0) + T.FLAP_DA)
         m = _af(T, ids, L.AF_CLMAX)
         return np.clip(cl, -m, m)
+    return _blend(T, _per_airfoil(T, T.afa, alpha, Re, M, lin, 0), _per_airfoil(T, T.afb, alpha, Re, M, lin, 0))
+
+
+def _section_CL_d(T, alpha, Re, M, dkind):
+    lin = (lambda ids: _af(T, ids, L.AF_CLA)) if dkind == 0 else (lambda ids: np.zeros(T.n))
+    return _blend(T, _per_airfoil(T, T.afa, alpha, Re, M, lin, 0, dkind), _per_airfoil(T, T.afb, alpha, Re, M, lin, 0, dkind))
+
+
+def section_CLa(T, alpha=None, Re=None, M=None):
+    z = _zeros(T)
+    return _section_CL_d(T, z if alpha is None else alpha, z if Re is None else Re, z if M is None else M, 0)
+
+
+def section_CLRe(T, alpha, Re, M):
+    return _section_CL_d(T, alpha, Re, M, 1)
+
+
+def section_CLM(T, alpha, Re, M):
+    return _section_CL_d(T, alpha, Re, M, 2)
+
+
+def section_aL0(T, Re=None, M=None):
+    Re = _zeros(T) if Re is None else Re
+    M = _zeros(T) if M is None else M
+
+    def one(ids):
+        out = _af(T, ids, L.AF_AL0) - T.FLAP_DA
+        for a in np.unique(ids):
+            if T.af[a, L.AF_TYPE] > 0.5:            # root of the CL fit in alpha by Newton's method from alpha = 0
+                mask = ids == a
+                a0 = np.zeros(T.n)
+                for _ in range(30):
+                    f = _poly_one(T, a, mask, a0, Re, M, 0, None)
+                    df = _poly_one(T, a, mask, a0, Re, M, 0, 0)
+                    step = f / df
+                    a0[mask] -= step
+                    if not (np.abs(step) > 1e-15).any():
+                        break
+                out = np.array(out, dtype=float)
+                out[mask] = a0[mask]
+        return out
     return _blend(T, one(T.afa), one(T.afb))
 
 
-def section_CLa(T):
-    return _blend(T, _af(T, T.afa, L.AF_CLA), _af(T, T.afb, L.AF_CLA))
+def section_CD(T, alpha, Re=None, M=None):
+    Re = _zeros(T) if Re is None else Re
+    M = _zeros(T) if M is None else M
 
-
-def section_aL0(T):
-    return _blend(T, _af(T, T.afa, L.AF_AL0) - T.FLAP_DA, _af(T, T.afb, L.AF_AL0) - T.FLAP_DA)
-
-
-def section_CD(T, alpha):
-    def one(ids):
+    def lin(ids):
         m = _af(T, ids, L.AF_CLMAX)
         cl = np.clip(_af(T, ids, L.AF_CLA) * (alpha - _af(T, ids, L.AF_AL0)), -m, m)
         return _af(T, ids, L.AF_CD0) + _af(T, ids, L.AF_CD1) * cl + _af(T, ids, L.AF_CD2) * cl * cl + T.FLAP_DCD
-    return _blend(T, one(T.afa), one(T.afb))
+    return _blend(T, _per_airfoil(T, T.afa, alpha, Re, M, lin, 1), _per_airfoil(T, T.afb, alpha, Re, M, lin, 1))
 
 
-def section_Cm(T, alpha):
-    def one(ids):
+def section_Cm(T, alpha, Re=None, M=None):
+    Re = _zeros(T) if Re is None else Re
+    M = _zeros(T) if M is None else M
+
+    def lin(ids):
         return _af(T, ids, L.AF_CMA) * (alpha - _af(T, ids, L.AF_AL0)) + _af(T, ids, L.AF_CML0) + T.FLAP_DCM
-    return _blend(T, one(T.afa), one(T.afb))
+    return _blend(T, _per_airfoil(T, T.afa, alpha, Re, M, lin, 2), _per_airfoil(T, T.afb, alpha, Re, M, lin, 2))
 
 
 # ------------------------------------------------------------------------------------------
@@ -262,9 +363,9 @@ def flow_state(T):
     v_n = np.einsum('ij,ij->i', F.v_inf_and_rot, T.UN)                        # scene.py:649-651
     v_a = np.einsum('ij,ij->i', F.v_inf_and_rot, T.UA)
     F.alpha_inf = np.arctan2(v_n, v_a)
-    F.CLa = section_CLa(T)                                                    # scene.py:659-661
-    F.CL = section_CL(T, F.alpha_inf)
-    F.aL0 = section_aL0(T)
+    F.CLa = section_CLa(T, F.alpha_inf, F.Re, F.M)                            # scene.py:659-661
+    F.CL = section_CL(T, F.alpha_inf, F.Re, F.M)
+    F.aL0 = section_aL0(T, F.Re, F.M)
     if T.swept:                                                               # scene.py:665-666, 797
         F.CL = F.CL + F.CLa * (F.aL0 - F.aL0 * T.CSWI)
     return F
@@ -389,10 +490,10 @@ def residual(T, F, V, gamma):
     S.v_a = np.einsum('ij,ij->i', S.v_i, T.UA)                                # scene.py:751-753
     S.v_n = np.einsum('ij,ij->i', S.v_i, T.UN)
     S.alpha = np.arctan2(S.v_n, S.v_a)
-    S.CLa = section_CLa(T)                                                    # scene.py:765-768
-    S.CL = section_CL(T, S.alpha)
-    S.CLRe = np.zeros(T.n)
-    S.CLM = np.zeros(T.n)
+    S.CLa = section_CLa(T, S.alpha, S.Re, S.M)                                # scene.py:765-768
+    S.CL = section_CL(T, S.alpha, S.Re, S.M)
+    S.CLRe = section_CLRe(T, S.alpha, S.Re, S.M)
+    S.CLM = section_CLM(T, S.alpha, S.Re, S.M)
     if T.match_pro:                                                           # scene.py:774-775
         L_section = F.V_inf * F.V_inf * S.CL * T.DS
     else:
@@ -502,8 +603,8 @@ def integrate(T, F, V, gamma):
     else:
         redim_full = 0.5 * T.RHO * F.V_inf * F.V_inf * T.DS
         redim_ip = 0.5 * T.RHO * F.V_inf_in_plane * F.V_inf_in_plane * T.DS if T.in_plane else None
-    CD = section_CD(T, alpha_unswept)                                         # scene.py:1014-1017
-    Cm = section_Cm(T, alpha)                                                 # scene.py:1020
+    CD = section_CD(T, alpha_unswept, Re_unswept, M)                          # scene.py:1014-1017
+    Cm = section_Cm(T, alpha, Re, M)                                          # scene.py:1020
     if T.swept:
         Cm = Cm * T.CSWI                                                      # scene.py:1026
     if T.in_plane:                                                            # scene.py:1029-1032
