@@ -21,6 +21,7 @@
 // No pivoting: the lifting-line matrices are dominated by the 2|w_i| diagonal (DESIGN.md "LU"); the
 // smallest pivot magnitude is tracked and zero/NaN pivots raise LLS_STATUS_NAN.
 #include "lls_internal.h"
+#include <cstdlib>
 
 namespace lls {
 
@@ -298,7 +299,10 @@ __device__ __forceinline__ void forward_rhs_warp(const double* __restrict__ sC, 
 // FIRST: no trailing update (factor block 0 and its panel); otherwise update with panel k and factor panel k+1.
 // Grid (1-D): block 0 = diag tile, 1..rem-1 = L tiles, rem..2rem-2 = U tiles, then the (rem-1)^2 others,
 // where rem = number of block rows/cols of the trailing matrix handled here.
-template <bool FIRST>
+// PASSES = 2: the trailing tiles take the updates of panels k AND k+1 in one visit (rank-128 update, half the traffic on C
+// and twice the tensor work per tile visit); the tiles of block row / column k+1 were brought up to date, and panel k+1
+// factored, by a thin PASSES = 1 launch just before.  The look-ahead roles then factor panel k + PASSES.
+template <bool FIRST, int PASSES>
 __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restrict__ M, int ld, int k, int rem,
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
     __shared__ __align__(16) double dinv[NB];
     const int t = threadIdx.x;
     const int b = blockIdx.x;
-    const int base = FIRST ? 0 : k + 1;  // first block row/col of the trailing matrix
+    const int base = FIRST ? 0 : k + PASSES;  // first block row/col of the trailing matrix handled here
     int bi, bj;
     enum { DIAG, LCOL, UROW, OTHER } role;
     if (b == 0) {
@@ -344,14 +348,22 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
         __syncthreads();
         LU_CLK(1);
         mma_tile(sA, sB, acc);                                                // -C + L U
+        if (PASSES == 2) {
+            __syncthreads();
+            load_tile_async(sA, M + (size_t)bi * NB * ld + (size_t)(k + 1) * NB, ld);   // L[bi,k+1]
+            load_tile_async(sB, M + (size_t)(k + 1) * NB * ld + (size_t)bj * NB, ld);   // U[k+1,bj]
+            async_wait_all();
+            __syncthreads();
+            mma_tile(sA, sB, acc);
+        }
         LU_CLK(2);
         if (role == OTHER) {
             acc_io<false>(acc, gC, ld);                                       // C - L U
             return;
         }
-        if (rhs != nullptr && bj == base && t < NB) {   // b[bi] -= L[bi,k] y_k
+        if (rhs != nullptr && bj == base && t < NB) {   // b[bi] -= L[bi,kk] y_kk for the last panel applied (the thin launch did the other)
             double s = 0.0;
-            const double* yk = rhs + (size_t)k * NB;
+            const double* yk = rhs + (size_t)(k + PASSES - 1) * NB;
 #pragma unroll 8
             for (int q = 0; q < NB; ++q) s = fma(sA[t * TS + q], yk[q], s);
             rhs[(size_t)bi * NB + t] -= s;
@@ -812,11 +824,16 @@ extern "C" int lls_debug_lu_clocks(long long* out16) {
 #endif
 
 static bool g_attr_done = false;
+constexpr int LU_PAIR_MIN_REM = 64;
+static bool g_lu_pairs = true;   // LLS_LU_PAIRS=0 falls back to one rank-64 update per launch
 
 static int lu_prepare(Scene* s) {
     if (!g_attr_done) {
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        const char* env = getenv("LLS_LU_PAIRS");
+        if (env != nullptr && env[0] == '0') g_lu_pairs = false;
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         g_attr_done = true;
     }
     (void)s;
@@ -847,15 +864,31 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     int* flags = s->lu_flags;
     {
         const int rem = nblk;       // block 0 and its panel
-        lu_step_kernel<true><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch,
-                                                                                                 s->scalars, s->status, cs);
+        lu_step_kernel<true, 1><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch,
+                                                                                                    s->scalars, s->status, cs);
         count_launch();
     }
-    for (int k = 0; k + 1 < nblk; ++k) {
+    for (int k = 0; k + 1 < nblk;) {
         const int rem = nblk - 1 - k;
-        lu_step_kernel<false><<<dim3(rem * rem, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch,
-                                                                                               s->scalars, s->status, cs);
-        count_launch();
+        // pairs pay off once the bulk of a launch outweighs the exposed chain of the thin launch (measured on B200: N = 16000
+        // 123 -> 113 ms, N = 8000 17.1 -> 16.5 ms, N = 4000 3.25 -> 3.33 ms when pairing everything)
+        if (rem >= LU_PAIR_MIN_REM && g_lu_pairs) {
+            // thin launch: block row / column k+1 only (update with panel k, factor panel k+1) ...
+            lu_step_kernel<false, 1><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags,
+                                                                                                         epoch, s->scalars, s->status, cs);
+            count_launch();
+            // ... then one visit of the rest with panels k and k+1 together, factoring panel k+2 on the way
+            const int rem2 = rem - 1;
+            lu_step_kernel<false, 2><<<dim3(rem2 * rem2, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem2, rhs, dbuf, s->uinv, flags,
+                                                                                                         epoch, s->scalars, s->status, cs);
+            count_launch();
+            k += 2;
+        } else {
+            lu_step_kernel<false, 1><<<dim3(rem * rem, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch,
+                                                                                                       s->scalars, s->status, cs);
+            count_launch();
+            k += 1;
+        }
     }
     if (rhs) {
         lu_backsolve_chain_kernel<<<dim3(nblk, 1, ncases), BS_THREADS, 0, st>>>(M, ld, nblk, s->uinv, rhs, x, s->lu_flags + nblk + 1, epoch, cs);
