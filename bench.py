@@ -365,7 +365,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"kernel": "lu_step_kernel: blocked FP64 LU factorisation, one launch per 64-column block step (trailing update on DMMA mma.sync m8n8k4, next panel factored in the same launch) + lu_backsolve_chain_kernel",
                      "bound": "tensor", "achieved": lu_tflops, "peak": fp64_dmma, "unit": "TFLOP/s",
-                     "frac": lu_tflops / fp64_dmma if fp64_dmma else None, "traffic": NCU_LU_TRAFFIC,
+                     "frac": lu_tflops / fp64_dmma if fp64_dmma else None, "traffic": NCU_LU_TRAFFIC["bytes_per_launch"],
+                     "traffic_detail": NCU_LU_TRAFFIC,
                      "peak_source": "FP64 DMMA probe run live by this process (MEASURED_PEAKS.json has no FP64 entry)",
                      "flops_per_solve": lu_flops, "ms_per_solve": lu_ms, "factorisations_per_solve": n_fact},
         "kernels": kernels,

@@ -10,7 +10,9 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/f_plain.json 2> gpurun_out/f_plain.err &&
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'lls::|lu_|influence|assemble|residual|integrate|flow_state|sum_kernel|newton|copy_gamma' -s 3500 -c 900 --csv --log-file gpurun_out/f_launches.csv $CMD > gpurun_out/f_ncu1.log 2>&1
 $CMD > /dev/null 2>&1 &&
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'influence_kernel|assemble_kernel|residual_kernel' -s 6 -c 4 -o gpurun_out/f_stream $CMD > gpurun_out/f_ncu2.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'assemble_kernel|residual_kernel' -s 6 -c 2 -o gpurun_out/f_stream $CMD > gpurun_out/f_ncu2.log 2>&1
+$CMD > /dev/null 2>&1 &&
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:influence_kernel -s 2 -c 1 -o gpurun_out/f_influence $CMD > gpurun_out/f_ncu4.log 2>&1
 $CMD > /dev/null 2>&1 &&
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:lu_step_kernel -s 198 -c 1 -o gpurun_out/f_lu $CMD > gpurun_out/f_ncu3.log 2>&1
 echo done
