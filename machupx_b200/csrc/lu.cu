@@ -53,19 +53,29 @@ __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
-// 64x64 tile global -> shared (row stride TS) with cp.async (16 bytes per request, all 16 requests of a thread in flight)
+// Everything below is written for CTAs of NT = 128 threads (4 warps, warp tile 32 x 32 of the 64 x 64 tile) or NT = 256 threads
+// (8 warps, warp tile 32 x 16).  In a 256-thread CTA the panel roles (factorisation, panel solves) still run on threads 0..127:
+// they meet at named barrier 1 (panel_sync) while the upper four warps wait at barrier 0.
+template <int NT>
+__device__ __forceinline__ void panel_sync() {
+    if (NT == 128) __syncthreads();
+    else asm volatile("bar.sync 1, 128;\n" ::: "memory");
+}
+
+// 64x64 tile global -> shared (row stride TS) with cp.async (16 bytes per request, all requests of a thread in flight)
+template <int NT = LU_THREADS>
 __device__ __forceinline__ void load_tile_async(double* __restrict__ s, const double* __restrict__ g, size_t ldg) {
     const int t = threadIdx.x;
     const int c2 = t & 31, r0 = t >> 5;
 #pragma unroll
-    for (int r = r0; r < NB; r += 4) {
+    for (int r = r0; r < NB; r += NT / 32) {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(s + r * TS + 2 * c2);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(g + (size_t)r * ldg + 2 * c2) : "memory");
     }
 }
 __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
-// shared (row stride TS) -> 64x64 tile in global memory, coalesced
+// shared (row stride TS) -> 64x64 tile in global memory, coalesced (threads 0..127)
 __device__ __forceinline__ void store_tile(double* __restrict__ g, size_t ldg, const double* __restrict__ s) {
     const int t = threadIdx.x;
     const int c2 = t & 31, r0 = t >> 5;
@@ -74,37 +84,47 @@ __device__ __forceinline__ void store_tile(double* __restrict__ g, size_t ldg, c
         *reinterpret_cast<double2*>(g + (size_t)r * ldg + 2 * c2) = *reinterpret_cast<const double2*>(s + r * TS + 2 * c2);
 }
 
-// acc (per warp 32x32 of the 64x64 tile) += sA(64 x 64, [m][k]) * sB(64 x 64, [k][n])
-__device__ __forceinline__ void mma_tile(const double* __restrict__ sA, const double* __restrict__ sB, double (&acc)[4][4][2]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+template <int NT>
+struct WarpTile {
+    static constexpr int NI = (NT == 128) ? 4 : 2;       // 8-column fragments per warp
+    __device__ static __forceinline__ int wm() { const int warp = threadIdx.x >> 5; return (NT == 128) ? (warp >> 1) * 32 : (warp >> 2) * 32; }
+    __device__ static __forceinline__ int wn() { const int warp = threadIdx.x >> 5; return (NT == 128) ? (warp & 1) * 32 : (warp & 3) * 16; }
+};
+
+// acc (per warp 32 x 32 or 32 x 16 of the 64x64 tile) += sA(64 x 64, [m][k]) * sB(64 x 64, [k][n])
+template <int NT = LU_THREADS>
+__device__ __forceinline__ void mma_tile(const double* __restrict__ sA, const double* __restrict__ sB, double (&acc)[4][WarpTile<NT>::NI][2]) {
+    constexpr int NI = WarpTile<NT>::NI;
+    const int lane = threadIdx.x & 31;
+    const int wm = WarpTile<NT>::wm(), wn = WarpTile<NT>::wn();
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll 4
     for (int k0 = 0; k0 < NB; k0 += 4) {
-        double a[4], b[4];
+        double a[4], b[NI];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(wm + mi * 8 + g) * TS + k0 + q];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = sB[(k0 + q) * TS + wn + ni * 8 + g];
+        for (int ni = 0; ni < NI; ++ni) b[ni] = sB[(k0 + q) * TS + wn + ni * 8 + g];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
 }
 
 // accumulator fragments <-> a row-major tile (global with ldg, or shared with TS)
 // LOAD negates on the way in and the store negates on the way out: the tile product is accumulated as
 // -(C) + L U, so neither operand tile needs a sign flip in shared memory
-template <bool LOAD>
-__device__ __forceinline__ void acc_io(double (&acc)[4][4][2], double* __restrict__ g, size_t ldg) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+template <bool LOAD, int NT = LU_THREADS>
+__device__ __forceinline__ void acc_io(double (&acc)[4][WarpTile<NT>::NI][2], double* __restrict__ g, size_t ldg) {
+    constexpr int NI = WarpTile<NT>::NI;
+    const int lane = threadIdx.x & 31;
+    const int wm = WarpTile<NT>::wm(), wn = WarpTile<NT>::wn();
     const int gq = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
+        for (int ni = 0; ni < NI; ++ni) {
             double2* p = reinterpret_cast<double2*>(g + (size_t)(wm + mi * 8 + gq) * ldg + wn + ni * 8 + 2 * q);
             if (LOAD) {
                 double2 v = *p;
@@ -142,7 +162,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return fma(x0, q, x0);
 }
 
-template <int J>
+template <int J, int NT>
 __device__ __forceinline__ void factor_group(double (&a)[4][8], PivotLine& pl, int ty, int tx) {
     constexpr int I = J >> 1;
     // compact rolled loop on purpose: these few hundred bytes of code run 8 times per group out of the instruction
@@ -172,7 +192,7 @@ __device__ __forceinline__ void factor_group(double (&a)[4][8], PivotLine& pl, i
             }
             if (I / 2 == 0) dst[1] = make_double2(a[2][J], a[3][J]);
         }
-        __syncthreads();
+        panel_sync<NT>();
         double r8[8], c4[4];
         {
             const double2* rr = reinterpret_cast<const double2*>(&pl.row[buf][tx * 8]);
@@ -204,6 +224,7 @@ __device__ __forceinline__ void factor_group(double (&a)[4][8], PivotLine& pl, i
     }
 }
 
+template <int NT = LU_THREADS>
 __device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine& pl) {
     const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
     double a[4][8];
@@ -211,15 +232,15 @@ __device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine&
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * TS + tx + 8 * j];
-    factor_group<0>(a, pl, ty, tx);
-    factor_group<1>(a, pl, ty, tx);
-    factor_group<2>(a, pl, ty, tx);
-    factor_group<3>(a, pl, ty, tx);
-    factor_group<4>(a, pl, ty, tx);
-    factor_group<5>(a, pl, ty, tx);
-    factor_group<6>(a, pl, ty, tx);
-    factor_group<7>(a, pl, ty, tx);
-    __syncthreads();      // pl.rcp complete
+    factor_group<0, NT>(a, pl, ty, tx);
+    factor_group<1, NT>(a, pl, ty, tx);
+    factor_group<2, NT>(a, pl, ty, tx);
+    factor_group<3, NT>(a, pl, ty, tx);
+    factor_group<4, NT>(a, pl, ty, tx);
+    factor_group<5, NT>(a, pl, ty, tx);
+    factor_group<6, NT>(a, pl, ty, tx);
+    factor_group<7, NT>(a, pl, ty, tx);
+    panel_sync<NT>();      // pl.rcp complete
     // registers hold U on and above the diagonal and the unscaled multipliers below it: L(r, c) = a(r, c) / U(c, c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -230,7 +251,7 @@ __device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine&
             sC[row * TS + col] = (row > col) ? a[i][j] * rc : a[i][j];
         }
     }
-    __syncthreads();
+    panel_sync<NT>();
 }
 
 // ---- X W = C for an upper-triangular W, in place on a 64 x 64 tile held in the same 2-D cyclic register layout -----
@@ -295,6 +316,129 @@ __device__ __forceinline__ void forward_rhs_warp(const double* __restrict__ sC, 
     b[lane + 32] = x1;
 }
 
+// ---- persistent trailing-update workers ----------------------------------------------------------------------------
+// The tiles of the trailing matrix that carry no panel role are walked in serpentine order (left to right on even tile
+// rows, right to left on odd ones), so two consecutive tiles always share the L tile or the U tile and exactly ONE 32 KB
+// operand has to arrive per tile.  A worker CTA owns three shared-memory slots (L, U, one being filled by cp.async for
+// the next tile) and keeps the next C tile in registers, so the loads of tile t+1 fly while tile t is on the tensor
+// pipe: the DMMA phases of a CTA run back to back instead of load -> mma -> store once per CTA.  Tiles are handed out
+// in chunks of consecutive serpentine indices through one atomic counter per block step; a worker grabs one chunk
+// ahead, so the counter's latency is hidden as well.  Panel-role CTAs join the same loop once their panel is done.
+struct UpdateGeom {
+    const double* L;   size_t l_stride;    // L tile of tile row r: L + r * l_stride, leading dimension ld
+    const double* U;   size_t u_stride;    // U tile of tile column c: U + c * u_stride, leading dimension ldu
+    size_t ldu;
+    double* C;                             // tile (r, c): C + (r * ld + c) * NB, leading dimension ld
+    size_t ld;
+    int rows, cols;
+};
+
+__device__ __forceinline__ void serpentine(int o, int cols, int& r, int& c) {
+    r = o / cols;
+    const int cc = o - r * cols;
+    c = (r & 1) ? (cols - 1 - cc) : cc;
+}
+
+template <int NT>
+__device__ __forceinline__ void c_prefetch(double2 (&cn)[4][WarpTile<NT>::NI], const double* __restrict__ g, size_t ldg) {
+    const int lane = threadIdx.x & 31;
+    const int wm = WarpTile<NT>::wm(), wn = WarpTile<NT>::wn();
+    const int gq = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < WarpTile<NT>::NI; ++ni)
+            cn[mi][ni] = *reinterpret_cast<const double2*>(g + (size_t)(wm + mi * 8 + gq) * ldg + wn + ni * 8 + 2 * q);
+}
+
+struct WorkerShared {
+    int first;
+    int ahead[2];
+};
+
+template <int NT>
+__device__ __forceinline__ void lu_update_worker(const UpdateGeom& G, int* __restrict__ counter, int chunk, double* __restrict__ sm,
+                                                 WorkerShared& ws) {
+    const int t = threadIdx.x;
+    const int T = G.rows * G.cols;
+    const int dbg = chunk >> 8;      // timing ablations (LLS_LU_WORKER_DBG): 1 no C stores, 2 no C loads, 4 no operand loads
+    chunk &= 255;
+    if (t == 0) {
+        ws.first = atomicAdd(counter, chunk);
+    }
+    __syncthreads();
+    int o = ws.first;
+    if (o >= T) return;
+    int oe = min(o + chunk, T);
+    int par = 0;                      // parity of the chunk being worked on: start of the next chunk is ws.ahead[par]
+    int sl = 0, su = 1, sf = 2;       // slots holding L, U, and the free one
+    int r, c;
+    serpentine(o, G.cols, r, c);
+    load_tile_async<NT>(sm + sl * (NB * TS), G.L + (size_t)r * G.l_stride, G.ld);
+    load_tile_async<NT>(sm + su * (NB * TS), G.U + (size_t)c * G.u_stride, G.ldu);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    constexpr int NI = WarpTile<NT>::NI;
+    double2 cn[4][NI];
+    c_prefetch<NT>(cn, G.C + ((size_t)r * G.ld + c) * NB, G.ld);
+    bool chunk_start = true;
+    while (true) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();              // operands of this tile visible; every warp is done with the previous tile's slots
+        // successor of this tile: next in the chunk, or the first tile of the chunk grabbed ahead
+        int no = o + 1;
+        if (no >= oe) no = chunk_start ? T : ws.ahead[par];       // (a one-tile chunk has nothing grabbed ahead yet: see below)
+        int pend = 0;
+        if (chunk_start && t == 0) pend = atomicAdd(counter, chunk);
+        if (chunk_start && o + 1 >= oe) {
+            // chunk of a single tile: the grab cannot hide behind the tile; take it synchronously
+            if (t == 0) ws.ahead[par] = pend;
+            __syncthreads();
+            no = ws.ahead[par];
+        }
+        const bool has_next = no < T;
+        int nr = r, nc = c;
+        bool both = false, newL = false;
+        if (has_next) {
+            serpentine(no, G.cols, nr, nc);
+            newL = (nr != r);
+            both = newL && (nc != c);
+            if (!(dbg & 4)) {
+                if (newL) load_tile_async<NT>(sm + sf * (NB * TS), G.L + (size_t)nr * G.l_stride, G.ld);
+                else load_tile_async<NT>(sm + sf * (NB * TS), G.U + (size_t)nc * G.u_stride, G.ldu);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        double acc[4][NI][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) {
+                acc[mi][ni][0] = -cn[mi][ni].x;
+                acc[mi][ni][1] = -cn[mi][ni].y;
+            }
+        if (has_next && !(dbg & 2)) c_prefetch<NT>(cn, G.C + ((size_t)nr * G.ld + nc) * NB, G.ld);
+        mma_tile<NT>(sm + sl * (NB * TS), sm + su * (NB * TS), acc);
+        if (!(dbg & 1)) acc_io<false, NT>(acc, G.C + ((size_t)r * G.ld + c) * NB, G.ld);
+        if (chunk_start && o + 1 < oe && t == 0) ws.ahead[par] = pend;   // read after the next tile's barrier at the earliest
+        if (!has_next) break;
+        if (newL) { const int x = sl; sl = sf; sf = x; } else { const int x = su; su = sf; sf = x; }
+        if (both) {
+            // chunk boundary that changes both operands: the old U slot is free only now
+            __syncthreads();
+            if (!(dbg & 4)) load_tile_async<NT>(sm + su * (NB * TS), G.U + (size_t)nc * G.u_stride, G.ldu);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        chunk_start = (no >= oe);
+        if (chunk_start) {
+            oe = min(no + chunk, T);
+            par ^= 1;
+        }
+        o = no;
+        r = nr;
+        c = nc;
+    }
+}
+
 // ---- one block step ------------------------------------------------------------------------------------
 // FIRST: no trailing update (factor block 0 and its panel); otherwise update with panel k and factor panel k+1.
 // Grid (1-D): block 0 = diag tile, 1..rem-1 = L tiles, rem..2rem-2 = U tiles, then the (rem-1)^2 others,
@@ -302,11 +446,17 @@ __device__ __forceinline__ void forward_rhs_warp(const double* __restrict__ sC, 
 // PASSES = 2: the trailing tiles take the updates of panels k AND k+1 in one visit (rank-128 update, half the traffic on C
 // and twice the tensor work per tile visit); the tiles of block row / column k+1 were brought up to date, and panel k+1
 // factored, by a thin PASSES = 1 launch just before.  The look-ahead roles then factor panel k + PASSES.
-template <bool FIRST, int PASSES>
-__global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restrict__ M, int ld, int k, int rem,
+// WORKERS: the tiles without a panel role are not mapped to CTAs; blocks >= 2 rem - 1 are persistent workers (and the panel
+// CTAs turn into workers when their panel is done), see lu_update_worker.  `counters` holds one work counter per block step,
+// zeroed by the FIRST launch of every factorisation.
+template <bool FIRST, int PASSES, bool WORKERS>
+__global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) lu_step_kernel(double* __restrict__ M, int ld, int k, int rem,
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
-                                                                double* __restrict__ scalars, int* __restrict__ status, CaseStrides cs) {
+                                                                double* __restrict__ scalars, int* __restrict__ status, CaseStrides cs,
+                                                                int* __restrict__ counters, int chunk) {
+    constexpr int NT = WORKERS ? 256 : LU_THREADS;   // threads per CTA; the panel roles always run on threads 0..127
+    static_assert(!(WORKERS && (FIRST || PASSES != 1)), "workers take one panel per visit");
     if (LLS_CASE_INACTIVE(cs)) return;
     M = case_ptr(M, cs.M);
     if (rhs != nullptr) rhs = case_work_ptr(rhs, cs.work);
@@ -320,9 +470,30 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
     double* sB = sm + NB * TS;
     __shared__ __align__(16) PivotLine pl;
     __shared__ __align__(16) double dinv[NB];
+    __shared__ WorkerShared wsh;
     const int t = threadIdx.x;
     const int b = blockIdx.x;
     const int base = FIRST ? 0 : k + PASSES;  // first block row/col of the trailing matrix handled here
+    if (FIRST && counters != nullptr && b == 0) {
+        counters = case_work_ptr(counters, cs.work);
+        for (int e = t; e <= ld / NB; e += LU_THREADS) counters[e] = 0;
+    }
+    UpdateGeom geom;
+    if (WORKERS) {
+        const size_t o = (size_t)(base + 1) * NB;
+        geom.L = M + o * ld + (size_t)k * NB;
+        geom.l_stride = (size_t)NB * ld;
+        geom.U = M + (size_t)k * NB * ld + o;
+        geom.u_stride = NB;
+        geom.ldu = ld;
+        geom.C = M + o * ld + o;
+        geom.ld = ld;
+        geom.rows = geom.cols = rem - 1;
+        if (b >= 2 * rem - 1) {
+            lu_update_worker<NT>(geom, counters + base, chunk, sm, wsh);
+            return;
+        }
+    }
     int bi, bj;
     enum { DIAG, LCOL, UROW, OTHER } role;
     if (b == 0) {
@@ -340,25 +511,25 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
     double* gC = M + (size_t)bi * NB * ld + (size_t)bj * NB;
     LU_CLK(0);
     if (!FIRST) {
-        double acc[4][4][2];
-        load_tile_async(sA, M + (size_t)bi * NB * ld + (size_t)k * NB, ld);   // L[bi,k]
-        load_tile_async(sB, M + (size_t)k * NB * ld + (size_t)bj * NB, ld);   // U[k,bj]
-        acc_io<true>(acc, gC, ld);                                            // -C
+        double acc[4][WarpTile<NT>::NI][2];
+        load_tile_async<NT>(sA, M + (size_t)bi * NB * ld + (size_t)k * NB, ld);   // L[bi,k]
+        load_tile_async<NT>(sB, M + (size_t)k * NB * ld + (size_t)bj * NB, ld);   // U[k,bj]
+        acc_io<true, NT>(acc, gC, ld);                                            // -C
         async_wait_all();
         __syncthreads();
         LU_CLK(1);
-        mma_tile(sA, sB, acc);                                                // -C + L U
+        mma_tile<NT>(sA, sB, acc);                                                // -C + L U
         if (PASSES == 2) {
             __syncthreads();
-            load_tile_async(sA, M + (size_t)bi * NB * ld + (size_t)(k + 1) * NB, ld);   // L[bi,k+1]
-            load_tile_async(sB, M + (size_t)(k + 1) * NB * ld + (size_t)bj * NB, ld);   // U[k+1,bj]
+            load_tile_async<NT>(sA, M + (size_t)bi * NB * ld + (size_t)(k + 1) * NB, ld);   // L[bi,k+1]
+            load_tile_async<NT>(sB, M + (size_t)(k + 1) * NB * ld + (size_t)bj * NB, ld);   // U[k+1,bj]
             async_wait_all();
             __syncthreads();
-            mma_tile(sA, sB, acc);
+            mma_tile<NT>(sA, sB, acc);
         }
         LU_CLK(2);
         if (role == OTHER) {
-            acc_io<false>(acc, gC, ld);                                       // C - L U
+            acc_io<false, NT>(acc, gC, ld);                                       // C - L U
             return;
         }
         if (rhs != nullptr && bj == base && t < NB) {   // b[bi] -= L[bi,kk] y_kk for the last panel applied (the thin launch did the other)
@@ -369,13 +540,14 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
             rhs[(size_t)bi * NB + t] -= s;
         }
         __syncthreads();
-        acc_io<false>(acc, sB, TS);   // C - L U, row-major in shared memory
+        acc_io<false, NT>(acc, sB, TS);   // C - L U, row-major in shared memory
         __syncthreads();
     } else {
-        load_tile_async(sB, gC, ld);
+        load_tile_async<NT>(sB, gC, ld);
         async_wait_all();
         __syncthreads();
     }
+    if (NT == LU_THREADS || t < LU_THREADS) {      // ---- panel roles: threads 0..127, barrier panel_sync<NT>() ----
     double* sC = sB;
     const int blk = base;                       // index of the diagonal block being factored
     // published image of the factored diagonal block (per parity), already in the padded shared-memory layout so that
@@ -385,16 +557,16 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
 
     if (role == DIAG) {
         LU_CLK(3);
-        factor_block(sC, pl);
+        factor_block<NT>(sC, pl);
         LU_CLK(4);
         if (t < NB) dinv[t] = 1.0 / sC[t * TS + t];
-        __syncthreads();
+        panel_sync<NT>();
         for (int e = t; e < NB * NB; e += LU_THREADS) {
             const int r = e >> 6, c = e & 63;
             const double v = sC[r * TS + c];
             sA[r * TS + c] = (c > r) ? v * dinv[r] : v;
         }
-        __syncthreads();
+        panel_sync<NT>();
         {
             double2* g0 = reinterpret_cast<double2*>(img);
             const double2* s0 = reinterpret_cast<const double2*>(sA);
@@ -403,7 +575,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
             if (t < NB) img[NB * TS + t] = dinv[t];
         }
         __threadfence();
-        __syncthreads();
+        panel_sync<NT>();
         if (t == 0) st_release(flags + blk, epoch);
         LU_CLK(5);
         // everything below is off the critical path of the panel CTAs
@@ -420,7 +592,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
                 pl.piv[t >> 5] = m;
             }
         }
-        __syncthreads();
+        panel_sync<NT>();
         if (t == 0) {
             const double m = fmin(pl.piv[0], pl.piv[1]);
             scalars[1] = (blk == 0) ? m : fmin(m, scalars[1]);
@@ -432,7 +604,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
         if (t == 0) {
             while (ld_acquire(flags + blk) != epoch) __nanosleep(32);
         }
-        __syncthreads();
+        panel_sync<NT>();
         const double2* g = reinterpret_cast<const double2*>(img);
         double2* sT2 = reinterpret_cast<double2*>(sA);
         double2 v[IMG2 / LU_THREADS];
@@ -442,7 +614,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
         for (int u = 0; u < IMG2 / LU_THREADS; ++u) sT2[t + u * LU_THREADS] = v[u];
         if (t < NB) dinv[t] = (role == UROW) ? 1.0 : __ldcg(img + NB * TS + t);
         // LCOL: W = U11 (scaled upper part, row-major); UROW (transposed problem): W = L11^T, W(p, c) = image[c][p]
-        __syncthreads();
+        panel_sync<NT>();
     }
     {
         // 2-D cyclic register tile: a[i][j] <-> (row ty + 16 i, col tx + 8 j) of X; UROW works on the transposed tile
@@ -464,16 +636,21 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_step_kernel(double* __restri
         if (role == UROW) panel_solve<true>(a, sA, dinv);
         else panel_solve<false>(a, sA, dinv);
         LU_CLK(7);
-        __syncthreads();   // everyone is done reading the tile (and, in the diag CTA, the factors for the right-hand side)
+        panel_sync<NT>();   // everyone is done reading the tile (and, in the diag CTA, the factors for the right-hand side)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
     }
-    __syncthreads();
+    panel_sync<NT>();
     if (role == DIAG) store_tile(uinv + (size_t)blk * NB * NB, NB, sC);
     else store_tile(gC, ld, sC);
     LU_CLK(8);
+    }   // panel roles
+    if (WORKERS && rem > 1) {
+        __syncthreads();      // the tile has left shared memory: the slots are the worker's now
+        lu_update_worker<NT>(geom, counters + base, chunk, sm, wsh);
+    }
 }
 
 // ---- block back-substitution as ONE launch: a chain of CTAs, one per block row --------------------------------
@@ -826,14 +1003,28 @@ extern "C" int lls_debug_lu_clocks(long long* out16) {
 static bool g_attr_done = false;
 constexpr int LU_PAIR_MIN_REM = 64;
 static bool g_lu_pairs = true;   // LLS_LU_PAIRS=0 falls back to one rank-64 update per launch
+static int g_worker_min_rem = 0;     // LLS_LU_WORKER_MIN_REM: trailing matrices of at least this many block rows use persistent workers (0 = never, the default: measured no faster than the tile-per-CTA kernel)
+static int g_worker_chunk = 2;       // LLS_LU_WORKER_CHUNK: consecutive serpentine tiles per grab
+static int g_sms = 148;
+static int g_worker_dbg = 0;
 
 static int lu_prepare(Scene* s) {
     if (!g_attr_done) {
         const char* env = getenv("LLS_LU_PAIRS");
         if (env != nullptr && env[0] == '0') g_lu_pairs = false;
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        env = getenv("LLS_LU_WORKER_MIN_REM");
+        if (env != nullptr) g_worker_min_rem = atoi(env);
+        env = getenv("LLS_LU_WORKER_CHUNK");
+        if (env != nullptr && atoi(env) >= 1) g_worker_chunk = atoi(env);
+        env = getenv("LLS_LU_WORKER_DBG");
+        if (env != nullptr) g_worker_dbg = atoi(env);
+        int dev = 0;
+        LLS_CUDA_TRY(cudaGetDevice(&dev));
+        LLS_CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_BYTES));
         g_attr_done = true;
     }
     (void)s;
@@ -862,30 +1053,43 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     const int epoch = ++s->lu_epoch;
     double* dbuf = s->inv;          // 2 x PUB_DOUBLES published diagonal factors
     int* flags = s->lu_flags;
+    int* counters = s->lu_flags + 2 * (nblk + 1);   // one work counter per block step (zeroed by the first launch)
+    const bool workers_ok = (ncases == 1) && g_worker_min_rem > 0;
     {
         const int rem = nblk;       // block 0 and its panel
-        lu_step_kernel<true, 1><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch,
-                                                                                                    s->scalars, s->status, cs);
+        lu_step_kernel<true, 1, false><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
+            M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0);
         count_launch();
     }
     for (int k = 0; k + 1 < nblk;) {
         const int rem = nblk - 1 - k;
+        if (workers_ok && rem >= g_worker_min_rem) {
+            // panel roles as CTAs 0 .. 2 rem - 2, everything else through persistent workers (two per SM)
+            const long long tiles = (long long)(rem - 1) * (rem - 1);
+            const long long chunks = (tiles + g_worker_chunk - 1) / g_worker_chunk;
+            const int nworkers = (int)(chunks < 2LL * g_sms ? chunks : 2LL * g_sms);
+            lu_step_kernel<false, 1, true><<<dim3(2 * rem - 1 + nworkers, 1, 1), 256, 3 * TILE_BYTES, st>>>(
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8));
+            count_launch();
+            k += 1;
+            continue;
+        }
         // pairs pay off once the bulk of a launch outweighs the exposed chain of the thin launch (measured on B200: N = 16000
         // 123 -> 113 ms, N = 8000 17.1 -> 16.5 ms, N = 4000 3.25 -> 3.33 ms when pairing everything)
         if (rem >= LU_PAIR_MIN_REM && g_lu_pairs) {
             // thin launch: block row / column k+1 only (update with panel k, factor panel k+1) ...
-            lu_step_kernel<false, 1><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags,
-                                                                                                         epoch, s->scalars, s->status, cs);
+            lu_step_kernel<false, 1, false><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0);
             count_launch();
             // ... then one visit of the rest with panels k and k+1 together, factoring panel k+2 on the way
             const int rem2 = rem - 1;
-            lu_step_kernel<false, 2><<<dim3(rem2 * rem2, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem2, rhs, dbuf, s->uinv, flags,
-                                                                                                         epoch, s->scalars, s->status, cs);
+            lu_step_kernel<false, 2, false><<<dim3(rem2 * rem2, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
+                M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0);
             count_launch();
             k += 2;
         } else {
-            lu_step_kernel<false, 1><<<dim3(rem * rem, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch,
-                                                                                                       s->scalars, s->status, cs);
+            lu_step_kernel<false, 1, false><<<dim3(rem * rem, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0);
             count_launch();
             k += 1;
         }
