@@ -26,8 +26,16 @@
 namespace lls {
 
 #ifdef LLS_LU_CLOCKS
-__device__ long long g_lu_clocks[16];
-#define LU_CLK(slot) do { if (role == DIAG && threadIdx.x == 0) g_lu_clocks[slot] = clock64(); } while (0)
+// debug build only (scripts/lu_clocks.py): clock64 stamps of the diag CTA (slots 0..8) and of the first L-panel CTA (slots 12..20)
+// of every block step, to see how long the serial chain takes when it shares its SMs with trailing-update CTAs
+__device__ long long g_lu_clocks[256][24];
+#define LU_CLK(slot)                                                                                  \
+    do {                                                                                              \
+        if (threadIdx.x == 0 && base < 256) {                                                         \
+            if (role == DIAG) g_lu_clocks[base][slot] = clock64();                                    \
+            else if (role == LCOL && bi == base + 1) g_lu_clocks[base][12 + slot] = clock64();        \
+        }                                                                                             \
+    } while (0)
 #else
 #define LU_CLK(slot) do { } while (0)
 #endif
@@ -316,6 +324,35 @@ __device__ __forceinline__ void forward_rhs_warp(const double* __restrict__ sC, 
     b[lane + 32] = x1;
 }
 
+// ---- keeping the serial chain's SM to itself ---------------------------------------------------------------------------
+// The in-register factorisation of the diagonal block is latency- and FP64-issue-bound on ONE CTA; trailing-update CTAs that
+// share its SM keep the FP64 pipe busy with DMMA and stretch it 2-3.5x (measured per block step with scripts/lu_clocks.py:
+// 22.8 k cycles alone, 40-80 k beside update CTAs), which then is the length of every launch whose trailing update is shorter.
+// So the diag CTA announces the SM it runs on, and an update CTA that finds itself on that SM parks (after its operand loads
+// are in flight, before it touches the tensor pipe) until the diagonal block is published.  At most two CTA slots idle for
+// the length of the factorisation; the rest of the machine is unaffected.
+struct ChainGuard {
+    int* diag_sm;      // word the diag CTA writes its tag to
+    const int* flag;   // publish flag of the diagonal block being factored in this launch
+    int epoch;
+    int tag;           // (epoch, block, SM id) of this CTA: equals *diag_sm iff the diag CTA of this launch runs on this SM
+};
+__device__ __forceinline__ int chain_tag(int epoch, int blk) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    return ((epoch & 0x1fff) << 18) | ((blk & 0x3ff) << 8) | (int)(smid & 0xff);
+}
+__device__ __forceinline__ void chain_announce(const ChainGuard& g) {     // diag CTA, one thread
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(g.diag_sm), "r"(g.tag) : "memory");
+}
+__device__ __forceinline__ void chain_yield(const ChainGuard& g) {        // update CTA, one thread
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(g.diag_sm) : "memory");
+    if (v == g.tag) {
+        while (ld_acquire(g.flag) != g.epoch) __nanosleep(128);
+    }
+}
+
 // ---- persistent trailing-update workers ----------------------------------------------------------------------------
 // The tiles of the trailing matrix that carry no panel role are walked in serpentine order (left to right on even tile
 // rows, right to left on odd ones), so two consecutive tiles always share the L tile or the U tile and exactly ONE 32 KB
@@ -358,7 +395,7 @@ struct WorkerShared {
 
 template <int NT>
 __device__ __forceinline__ void lu_update_worker(const UpdateGeom& G, int* __restrict__ counter, int chunk, double* __restrict__ sm,
-                                                 WorkerShared& ws) {
+                                                 WorkerShared& ws, const ChainGuard& guard) {
     const int t = threadIdx.x;
     const int T = G.rows * G.cols;
     const int dbg = chunk >> 8;      // timing ablations (LLS_LU_WORKER_DBG): 1 no C stores, 2 no C loads, 4 no operand loads
@@ -381,8 +418,11 @@ __device__ __forceinline__ void lu_update_worker(const UpdateGeom& G, int* __res
     double2 cn[4][NI];
     c_prefetch<NT>(cn, G.C + ((size_t)r * G.ld + c) * NB, G.ld);
     bool chunk_start = true;
+    bool first_tile = true;
     while (true) {
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (first_tile && t == 0 && guard.diag_sm != nullptr) chain_yield(guard);
+        first_tile = false;
         __syncthreads();              // operands of this tile visible; every warp is done with the previous tile's slots
         // successor of this tile: next in the chunk, or the first tile of the chunk grabbed ahead
         int no = o + 1;
@@ -454,9 +494,13 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
                                                                 double* __restrict__ scalars, int* __restrict__ status, CaseStrides cs,
-                                                                int* __restrict__ counters, int chunk) {
+                                                                int* __restrict__ counters, int chunk, int nworkers, int* __restrict__ diag_sm) {
     constexpr int NT = WORKERS ? 256 : LU_THREADS;   // threads per CTA; the panel roles always run on threads 0..127
     static_assert(!(WORKERS && (FIRST || PASSES != 1)), "workers take one panel per visit");
+    // programmatic dependent launch: the CTAs of block step k+1 are placed on the SMs while step k drains and start the moment
+    // its memory is visible, instead of paying the launch latency between two launches of the chain (no-ops in a plain launch)
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     if (LLS_CASE_INACTIVE(cs)) return;
     M = case_ptr(M, cs.M);
     if (rhs != nullptr) rhs = case_work_ptr(rhs, cs.work);
@@ -478,6 +522,12 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         counters = case_work_ptr(counters, cs.work);
         for (int e = t; e <= ld / NB; e += LU_THREADS) counters[e] = 0;
     }
+    ChainGuard guard;
+    guard.diag_sm = (diag_sm != nullptr) ? case_work_ptr(diag_sm, cs.work) : nullptr;
+    guard.flag = flags + base;
+    guard.epoch = epoch;
+    guard.tag = chain_tag(epoch, base);
+    if (b == 0 && t == 0 && guard.diag_sm != nullptr) chain_announce(guard);
     UpdateGeom geom;
     if (WORKERS) {
         const size_t o = (size_t)(base + 1) * NB;
@@ -489,22 +539,25 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         geom.C = M + o * ld + o;
         geom.ld = ld;
         geom.rows = geom.cols = rem - 1;
-        if (b >= 2 * rem - 1) {
-            lu_update_worker<NT>(geom, counters + base, chunk, sm, wsh);
+        // grid order: diag CTA, `nworkers` workers, then the panel tiles.  The panel CTAs that do not fit beside the workers start
+        // when slots free up, find the diagonal block published long ago and never spin; the few that start at once do the waiting
+        if (b >= 1 && b <= nworkers) {
+            lu_update_worker<NT>(geom, counters + base, chunk, sm, wsh, guard);
             return;
         }
     }
+    const int pb = (WORKERS && b > 0) ? b - nworkers : b;     // index among the panel roles
     int bi, bj;
     enum { DIAG, LCOL, UROW, OTHER } role;
-    if (b == 0) {
+    if (pb == 0) {
         role = DIAG; bi = base; bj = base;
-    } else if (b < rem) {
-        role = LCOL; bi = base + b; bj = base;
-    } else if (b < 2 * rem - 1) {
-        role = UROW; bi = base; bj = base + (b - rem + 1);
+    } else if (pb < rem) {
+        role = LCOL; bi = base + pb; bj = base;
+    } else if (pb < 2 * rem - 1) {
+        role = UROW; bi = base; bj = base + (pb - rem + 1);
     } else {
         role = OTHER;
-        const int o = b - (2 * rem - 1);
+        const int o = pb - (2 * rem - 1);
         bi = base + 1 + o / (rem - 1);
         bj = base + 1 + o % (rem - 1);
     }
@@ -516,6 +569,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         load_tile_async<NT>(sB, M + (size_t)k * NB * ld + (size_t)bj * NB, ld);   // U[k,bj]
         acc_io<true, NT>(acc, gC, ld);                                            // -C
         async_wait_all();
+        if (role == OTHER && t == 0 && guard.diag_sm != nullptr) chain_yield(guard);
         __syncthreads();
         LU_CLK(1);
         mma_tile<NT>(sA, sB, acc);                                                // -C + L U
@@ -649,7 +703,9 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
     }   // panel roles
     if (WORKERS && rem > 1) {
         __syncthreads();      // the tile has left shared memory: the slots are the worker's now
-        lu_update_worker<NT>(geom, counters + base, chunk, sm, wsh);
+        ChainGuard none = guard;
+        none.diag_sm = nullptr;       // the panel of this launch is done
+        lu_update_worker<NT>(geom, counters + base, chunk, sm, wsh, none);
     }
 }
 
@@ -995,8 +1051,8 @@ __global__ void __launch_bounds__(256) lu_dist_back_kernel(const double* __restr
 }
 
 #ifdef LLS_LU_CLOCKS
-extern "C" int lls_debug_lu_clocks(long long* out16) {
-    return cudaMemcpyFromSymbol(out16, g_lu_clocks, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+extern "C" int lls_debug_lu_clocks(long long* out, int steps) {
+    return cudaMemcpyFromSymbol(out, g_lu_clocks, sizeof(long long) * 24 * (size_t)(steps < 256 ? steps : 256)) == cudaSuccess ? 0 : 1;
 }
 #endif
 
@@ -1007,6 +1063,25 @@ static int g_worker_min_rem = 0;     // LLS_LU_WORKER_MIN_REM: trailing matrices
 static int g_worker_chunk = 2;       // LLS_LU_WORKER_CHUNK: consecutive serpentine tiles per grab
 static int g_sms = 148;
 static int g_worker_dbg = 0;
+static bool g_chain_guard = true;     // LLS_LU_CHAIN_GUARD=0: update CTAs do not yield the diag CTA's SM
+static int g_worker_reserve = 48;     // LLS_LU_WORKER_RESERVE: CTA slots left to the panel tiles at the start of a launch
+
+static bool g_lu_pdl = true;          // LLS_LU_PDL=0: plain stream-ordered launches of the block steps
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_step(void (*kern)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_lu_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static int lu_prepare(Scene* s) {
     if (!g_attr_done) {
@@ -1016,6 +1091,12 @@ static int lu_prepare(Scene* s) {
         if (env != nullptr) g_worker_min_rem = atoi(env);
         env = getenv("LLS_LU_WORKER_CHUNK");
         if (env != nullptr && atoi(env) >= 1) g_worker_chunk = atoi(env);
+        env = getenv("LLS_LU_PDL");
+        if (env != nullptr && env[0] == '0') g_lu_pdl = false;
+        env = getenv("LLS_LU_CHAIN_GUARD");
+        if (env != nullptr && env[0] == '0') g_chain_guard = false;
+        env = getenv("LLS_LU_WORKER_RESERVE");
+        if (env != nullptr) g_worker_reserve = atoi(env);
         env = getenv("LLS_LU_WORKER_DBG");
         if (env != nullptr) g_worker_dbg = atoi(env);
         int dev = 0;
@@ -1054,11 +1135,12 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     double* dbuf = s->inv;          // 2 x PUB_DOUBLES published diagonal factors
     int* flags = s->lu_flags;
     int* counters = s->lu_flags + 2 * (nblk + 1);   // one work counter per block step (zeroed by the first launch)
+    int* diag_sm = g_chain_guard ? s->lu_flags + 3 * (nblk + 1) : nullptr;   // where the diag CTA announces its SM
     const bool workers_ok = (ncases == 1) && g_worker_min_rem > 0;
     {
         const int rem = nblk;       // block 0 and its panel
-        lu_step_kernel<true, 1, false><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
-            M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0);
+        LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false>, dim3(2 * rem - 1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm));
         count_launch();
     }
     for (int k = 0; k + 1 < nblk;) {
@@ -1067,9 +1149,11 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             // panel roles as CTAs 0 .. 2 rem - 2, everything else through persistent workers (two per SM)
             const long long tiles = (long long)(rem - 1) * (rem - 1);
             const long long chunks = (tiles + g_worker_chunk - 1) / g_worker_chunk;
-            const int nworkers = (int)(chunks < 2LL * g_sms ? chunks : 2LL * g_sms);
-            lu_step_kernel<false, 1, true><<<dim3(2 * rem - 1 + nworkers, 1, 1), 256, 3 * TILE_BYTES, st>>>(
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8));
+            long long nworkers = 2LL * g_sms - 1 - g_worker_reserve;      // resident CTAs: diag + workers + `reserve` panel CTAs
+            if (nworkers > chunks) nworkers = chunks;
+            if (nworkers < 1) nworkers = 1;
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, true>, dim3(2 * rem - 1 + (int)nworkers, 1, 1), 256, (size_t)3 * TILE_BYTES, st,
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8), (int)nworkers, diag_sm));
             count_launch();
             k += 1;
             continue;
@@ -1078,18 +1162,18 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
         // 123 -> 113 ms, N = 8000 17.1 -> 16.5 ms, N = 4000 3.25 -> 3.33 ms when pairing everything)
         if (rem >= LU_PAIR_MIN_REM && g_lu_pairs) {
             // thin launch: block row / column k+1 only (update with panel k, factor panel k+1) ...
-            lu_step_kernel<false, 1, false><<<dim3(2 * rem - 1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0);
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(2 * rem - 1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm));
             count_launch();
             // ... then one visit of the rest with panels k and k+1 together, factoring panel k+2 on the way
             const int rem2 = rem - 1;
-            lu_step_kernel<false, 2, false><<<dim3(rem2 * rem2, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
-                M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0);
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 2, false>, dim3(rem2 * rem2, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm));
             count_launch();
             k += 2;
         } else {
-            lu_step_kernel<false, 1, false><<<dim3(rem * rem, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0);
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(rem * rem, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm));
             count_launch();
             k += 1;
         }
