@@ -18,7 +18,7 @@ static size_t work_bytes_for(int ld) {
     b += align_up((size_t)W_NF * ld * 8, 256);
     b += align_up((size_t)LU_PUB_BYTES, 256);               // published diagonal LU block images (x2)
     b += align_up((size_t)ld * LU_NB * 8, 256);             // inverse diagonal U blocks
-    b += align_up((size_t)4 * (ld / LU_NB + 1) * 4, 256);   // LU flags (factorisation, back-substitution), work counters, diag-SM word
+    b += align_up((size_t)6 * (ld / LU_NB + 1) * 4, 256);   // LU flags (factorisation, back-substitution), work counters, diag-SM word, role claims
     b += align_up((size_t)ld * 8, 256);  // partial
     b += 256;                            // scalars
     b += 256;                            // status
@@ -152,14 +152,14 @@ extern "C" int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab
     h->uinv = (double*)p;
     p += align_up((size_t)h->ld * LU_NB * 8, 256);
     h->lu_flags = (int*)p;
-    p += align_up((size_t)4 * (h->ld / LU_NB + 1) * 4, 256);
+    p += align_up((size_t)6 * (h->ld / LU_NB + 1) * 4, 256);
     h->partial = (double*)p;
     p += align_up((size_t)h->ld * 8, 256);
     h->scalars = (double*)p;
     p += 256;
     h->status = (int*)p;
     // the LU's publish flags compare against a per-handle epoch that starts at 0: clear them once here
-    LLS_CUDA_TRY(cudaMemset(h->lu_flags, 0, (size_t)4 * (h->ld / LU_NB + 1) * 4));
+    LLS_CUDA_TRY(cudaMemset(h->lu_flags, 0, (size_t)6 * (h->ld / LU_NB + 1) * 4));
     h->lu_epoch = 0;
     LLS_CUDA_TRY(cudaMemset(h->inv, 0, LU_PUB_BYTES));       // includes the accumulator / ticket of the partitioned back substitution
     h->ncases = 1;
@@ -189,7 +189,7 @@ extern "C" int lls_bind_batch(lls_scene* h, int ncases, const double* d_tab, con
     h->cs.work = work_bytes_per_case;
     h->ctl = d_ctl;
     // LU publish flags of every case start below any epoch
-    LLS_CUDA_TRY(cudaMemset2D(h->lu_flags, work_bytes_per_case, 0, (size_t)4 * (h->ld / LU_NB + 1) * 4, (size_t)ncases));
+    LLS_CUDA_TRY(cudaMemset2D(h->lu_flags, work_bytes_per_case, 0, (size_t)6 * (h->ld / LU_NB + 1) * 4, (size_t)ncases));
     LLS_CUDA_TRY(cudaMemset(d_ctl, 0, sizeof(int) * (2 * (size_t)ncases + 4)));
     return LLS_OK;
 }

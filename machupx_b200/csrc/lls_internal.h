@@ -102,7 +102,7 @@ struct Scene {
     double* W = nullptr;        // W_NF * ld
     double* inv = nullptr;      // LU_PUB_BYTES: factored diagonal block images published by the LU's diag CTA (double-buffered)
     double* uinv = nullptr;     // ld * LU_NB: inverse of every diagonal U block, left by the factorisation for the back-substitution chain
-    int* lu_flags = nullptr;    // 4 * (ld / LU_NB + 1) ints ([3 (nblk + 1)] = SM announced by the diag CTA): [k] == lu_epoch once diagonal block k is published; [nblk + 1 + k] once x_k is; [2 (nblk + 1) + k] work counter of block step k
+    int* lu_flags = nullptr;    // 6 * (ld / LU_NB + 1) ints ([3 (nblk + 1)] = SM announced by the diag CTA, [4 (nblk + 1) + 2 k] role claims of step k): [k] == lu_epoch once diagonal block k is published; [nblk + 1 + k] once x_k is; [2 (nblk + 1) + k] work counter of block step k
     int lu_epoch = 0;           // factorisation counter (host)
     double* partial = nullptr;  // reduction scratch (>= 4096 doubles)
     double* scalars = nullptr;  // [0] ||R||^2  [1] min |pivot| ...   (device)

@@ -144,6 +144,33 @@ __device__ __forceinline__ void acc_io(double (&acc)[4][WarpTile<NT>::NI][2], do
         }
 }
 
+// The C tile of a trailing update as raw fragments, fetched with volatile loads so they are ISSUED where they are written (ahead
+// of the operand copies): ptxas otherwise sinks plain loads below the cp.async wait and the two memory latencies of a tile
+// (operands, then C) add up instead of overlapping.
+template <int NT = LU_THREADS>
+__device__ __forceinline__ void c_fetch(double2 (&cn)[4][WarpTile<NT>::NI], const double* __restrict__ g, size_t ldg) {
+    const int lane = threadIdx.x & 31;
+    const int wm = WarpTile<NT>::wm(), wn = WarpTile<NT>::wn();
+    const int gq = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < WarpTile<NT>::NI; ++ni) {
+            const double* p = g + (size_t)(wm + mi * 8 + gq) * ldg + wn + ni * 8 + 2 * q;
+            asm volatile("ld.global.v2.f64 {%0, %1}, [%2];\n" : "=d"(cn[mi][ni].x), "=d"(cn[mi][ni].y) : "l"(p) : "memory");
+        }
+}
+template <int NT = LU_THREADS>
+__device__ __forceinline__ void c_negate(double (&acc)[4][WarpTile<NT>::NI][2], const double2 (&cn)[4][WarpTile<NT>::NI]) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < WarpTile<NT>::NI; ++ni) {
+            acc[mi][ni][0] = -cn[mi][ni].x;
+            acc[mi][ni][1] = -cn[mi][ni].y;
+        }
+}
+
 // ---- in-CTA factorisation of a 64 x 64 block held in shared memory (row stride TS) -------------------
 // 128 threads as a 16 x 8 grid; thread (ty, tx) keeps rows ty + 16 i (i < 4) and columns tx + 8 j (j < 8) in
 // registers (cyclic, so the shrinking active window stays balanced).  Per pivot p the owners of row p and column p
@@ -494,7 +521,8 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
                                                                 double* __restrict__ scalars, int* __restrict__ status, CaseStrides cs,
-                                                                int* __restrict__ counters, int chunk, int nworkers, int* __restrict__ diag_sm) {
+                                                                int* __restrict__ counters, int chunk, int nworkers, int* __restrict__ diag_sm,
+                                                                int* __restrict__ claims, int panel_sms) {
     constexpr int NT = WORKERS ? 256 : LU_THREADS;   // threads per CTA; the panel roles always run on threads 0..127
     static_assert(!(WORKERS && (FIRST || PASSES != 1)), "workers take one panel per visit");
     // programmatic dependent launch: the CTAs of block step k+1 are placed on the SMs while step k drains and start the moment
@@ -518,9 +546,15 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
     const int t = threadIdx.x;
     const int b = blockIdx.x;
     const int base = FIRST ? 0 : k + PASSES;  // first block row/col of the trailing matrix handled here
-    if (FIRST && counters != nullptr && b == 0) {
-        counters = case_work_ptr(counters, cs.work);
-        for (int e = t; e <= ld / NB; e += LU_THREADS) counters[e] = 0;
+    if (FIRST && b == 0) {      // per-factorisation counters: worker chunks, role claims (two per block step)
+        if (counters != nullptr) {
+            counters = case_work_ptr(counters, cs.work);
+            for (int e = t; e <= ld / NB; e += LU_THREADS) counters[e] = 0;
+        }
+        if (claims != nullptr) {
+            int* c = case_work_ptr(claims, cs.work);
+            for (int e = t; e < 2 * (ld / NB + 1); e += LU_THREADS) c[e] = 0;
+        }
     }
     ChainGuard guard;
     guard.diag_sm = (diag_sm != nullptr) ? case_work_ptr(diag_sm, cs.work) : nullptr;
@@ -546,7 +580,33 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
             return;
         }
     }
-    const int pb = (WORKERS && b > 0) ? b - nworkers : b;     // index among the panel roles
+    // index among the roles: 0 diag, 1 .. 2 rem - 2 the L and U panel tiles, then the other tiles
+    int pb = (WORKERS && b > 0) ? b - nworkers : b;     // (WORKERS: the panel roles follow the workers in the grid)
+    if (!WORKERS && !FIRST && claims != nullptr && b > 0) {
+        // Roles by SM instead of by block index: CTAs that land on the first `panel_sms` SMs take the panel tiles (three to an SM),
+        // everybody else the update tiles; each side falls back to the other queue when its own is empty, and as the grid has
+        // exactly one CTA per tile every tile is taken.  The latency-bound panel solves then share their SMs with each other (they
+        // spin or run dependent FP64 chains) instead of with DMMA streams that stretch them 2-3x, and the update tiles get SMs
+        // whose tensor pipe they do not have to share with the chain.
+        __shared__ int s_role;
+        if (t == 0) {
+            claims = case_work_ptr(claims, cs.work) + 2 * base;
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int P = 2 * rem - 2, T = (rem - 1) * (rem - 1);
+            int idx;
+            if ((int)smid < panel_sms) {
+                const int p = atomicAdd(claims, 1);
+                idx = (p < P) ? 1 + p : 1 + P + atomicAdd(claims + 1, 1);
+            } else {
+                const int o = atomicAdd(claims + 1, 1);
+                idx = (o < T) ? 1 + P + o : 1 + atomicAdd(claims, 1);
+            }
+            s_role = idx;
+        }
+        __syncthreads();
+        pb = s_role;
+    }
     int bi, bj;
     enum { DIAG, LCOL, UROW, OTHER } role;
     if (pb == 0) {
@@ -565,11 +625,15 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
     LU_CLK(0);
     if (!FIRST) {
         double acc[4][WarpTile<NT>::NI][2];
-        load_tile_async<NT>(sA, M + (size_t)bi * NB * ld + (size_t)k * NB, ld);   // L[bi,k]
-        load_tile_async<NT>(sB, M + (size_t)k * NB * ld + (size_t)bj * NB, ld);   // U[k,bj]
-        acc_io<true, NT>(acc, gC, ld);                                            // -C
-        async_wait_all();
-        if (role == OTHER && t == 0 && guard.diag_sm != nullptr) chain_yield(guard);
+        {
+            double2 cn[4][WarpTile<NT>::NI];
+            c_fetch<NT>(cn, gC, ld);                                                  // C, in flight together with ...
+            load_tile_async<NT>(sA, M + (size_t)bi * NB * ld + (size_t)k * NB, ld);   // L[bi,k]
+            load_tile_async<NT>(sB, M + (size_t)k * NB * ld + (size_t)bj * NB, ld);   // U[k,bj]
+            async_wait_all();
+            if (role == OTHER && t == 0 && guard.diag_sm != nullptr) chain_yield(guard);
+            c_negate<NT>(acc, cn);                                                    // -C
+        }
         __syncthreads();
         LU_CLK(1);
         mma_tile<NT>(sA, sB, acc);                                                // -C + L U
@@ -996,10 +1060,14 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_update_kernel(double* _
     const int jj = blockIdx.x % ncols;                 // block column k + 1 + jj
     double* gC = Mloc + (size_t)lb * NB * ld + (size_t)(k + 1 + jj) * NB;
     double acc[4][4][2];
-    load_tile_async(sA, Mloc + (size_t)lb * NB * ld + (size_t)k * NB, ld);
-    load_tile_async(sB, utiles + (size_t)jj * NB * NB, NB);
-    acc_io<true>(acc, gC, ld);
-    async_wait_all();
+    {
+        double2 cn[4][4];
+        c_fetch(cn, gC, ld);
+        load_tile_async(sA, Mloc + (size_t)lb * NB * ld + (size_t)k * NB, ld);
+        load_tile_async(sB, utiles + (size_t)jj * NB * NB, NB);
+        async_wait_all();
+        c_negate(acc, cn);
+    }
     __syncthreads();
     mma_tile(sA, sB, acc);
     acc_io<false>(acc, gC, ld);
@@ -1066,6 +1134,7 @@ static int g_worker_dbg = 0;
 static bool g_chain_guard = true;     // LLS_LU_CHAIN_GUARD=0: update CTAs do not yield the diag CTA's SM
 static int g_worker_reserve = 48;     // LLS_LU_WORKER_RESERVE: CTA slots left to the panel tiles at the start of a launch
 
+static int g_pack_min_rem = 0;        // LLS_LU_PACK_MIN_REM: trailing matrices of at least this many block rows claim roles by SM (0 = never, the default: the claim at CTA start costs more than the isolation returns, 2.83 -> 2.95 ms at N = 4000)
 static bool g_lu_pdl = true;          // LLS_LU_PDL=0: plain stream-ordered launches of the block steps
 
 template <class... KArgs, class... Args>
@@ -1091,6 +1160,8 @@ static int lu_prepare(Scene* s) {
         if (env != nullptr) g_worker_min_rem = atoi(env);
         env = getenv("LLS_LU_WORKER_CHUNK");
         if (env != nullptr && atoi(env) >= 1) g_worker_chunk = atoi(env);
+        env = getenv("LLS_LU_PACK_MIN_REM");
+        if (env != nullptr) g_pack_min_rem = atoi(env);
         env = getenv("LLS_LU_PDL");
         if (env != nullptr && env[0] == '0') g_lu_pdl = false;
         env = getenv("LLS_LU_CHAIN_GUARD");
@@ -1136,11 +1207,12 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     int* flags = s->lu_flags;
     int* counters = s->lu_flags + 2 * (nblk + 1);   // one work counter per block step (zeroed by the first launch)
     int* diag_sm = g_chain_guard ? s->lu_flags + 3 * (nblk + 1) : nullptr;   // where the diag CTA announces its SM
+    int* claims = s->lu_flags + 4 * (nblk + 1);     // two role-claim counters per block step (zeroed by the first launch)
     const bool workers_ok = (ncases == 1) && g_worker_min_rem > 0;
     {
         const int rem = nblk;       // block 0 and its panel
         LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false>, dim3(2 * rem - 1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm));
+                M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0));
         count_launch();
     }
     for (int k = 0; k + 1 < nblk;) {
@@ -1153,7 +1225,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             if (nworkers > chunks) nworkers = chunks;
             if (nworkers < 1) nworkers = 1;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, true>, dim3(2 * rem - 1 + (int)nworkers, 1, 1), 256, (size_t)3 * TILE_BYTES, st,
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8), (int)nworkers, diag_sm));
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8), (int)nworkers, diag_sm, nullptr, 0));
             count_launch();
             k += 1;
             continue;
@@ -1163,17 +1235,19 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
         if (rem >= LU_PAIR_MIN_REM && g_lu_pairs) {
             // thin launch: block row / column k+1 only (update with panel k, factor panel k+1) ...
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(2 * rem - 1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm));
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0));
             count_launch();
             // ... then one visit of the rest with panels k and k+1 together, factoring panel k+2 on the way
             const int rem2 = rem - 1;
+            const int psm2 = (g_pack_min_rem > 0 && rem2 >= g_pack_min_rem) ? (2 * rem2 - 2 + 2) / 3 : 0;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 2, false>, dim3(rem2 * rem2, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm));
+                M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm2 ? claims : nullptr, psm2));
             count_launch();
             k += 2;
         } else {
+            const int psm = (g_pack_min_rem > 0 && rem >= g_pack_min_rem) ? (2 * rem - 2 + 2) / 3 : 0;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(rem * rem, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm));
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm ? claims : nullptr, psm));
             count_launch();
             k += 1;
         }
