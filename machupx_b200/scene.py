@@ -455,8 +455,14 @@ class Scene:
         finally:
             ap.v, ap.w, ap.p_bar, ap.q = saved
             ap.angular_rate_frame = saved_frame
-        ac_states = np.array(rows)
-        n_total = len(states)
+        return self._solve_batch_rows(np.array(rows), max_batch)
+
+    def _solve_batch_rows(self, ac_states, max_batch=4096):
+        """Device part of a batch: ``ac_states`` (ncases, n_aircraft, AC_STRIDE) per-aircraft state blocks as build_aircraft_state
+        makes them, all for the geometry the scene currently has."""
+        from .device import BatchDeviceScene
+        from .forces import batch_totals
+        n_total = len(ac_states)
         info = []
         seg0 = 0
         for a in self._airplane_objects:
@@ -575,9 +581,10 @@ class Scene:
             sub = dict(kwargs)
             sub["aircraft"] = name
             sub.pop("filename", None)
+            seq = {k: v for k, v in sub.items() if k != "batched"}      # flap deflections live in the shared tables: sequential
             derivs[name] = {"stability": self.stability_derivatives(**sub)[name],
                             "damping": self.damping_derivatives(**sub)[name],
-                            "control": self.control_derivatives(**sub)[name]}
+                            "control": self.control_derivatives(**seq)[name]}
         filename = kwargs.get("filename", None)
         if filename is not None:
             with open(filename, "w") as handle:
@@ -589,13 +596,58 @@ class Scene:
         self.solve_forces(dimensional=False, **kw)
         return self._FM
 
+    def _stencil_totals(self, name, setters):
+        """Totals of a finite-difference stencil as ONE batched device pass: every callable of
+        ``setters`` perturbs the airplane ``name`` starting from its current state (velocity / angular rates only: the
+        geometry tables are shared by the cases); returns one {key: float} dictionary of aircraft totals per case, with the
+        body- and wind-frame keys of ``_FM[name]["total"]``."""
+        ap = self._airplanes[name]
+        if self._current_pose_key() != self._pose_key:
+            self._perform_geometry_and_atmos_calcs()
+        saved = ap.get_state()
+        rows = []
+        try:
+            for perturb in setters:
+                perturb(ap)
+                rows.append(build_aircraft_state(self))
+                ap.v, ap.w, ap.p_bar, ap.q = (np.copy(x) for x in saved)
+        finally:
+            ap.v, ap.w, ap.p_bar, ap.q = saved
+        tot = self._solve_batch_rows(np.array(rows))["totals"][name]
+        return [{k: float(v[i]) for k, v in tot.items()} for i in range(len(setters))]
+
+    def _batched_ok(self, kwargs):
+        """``batched=True`` runs a derivative stencil as one batch; the stability-frame keys are not part of the batch totals."""
+        if not kwargs.get("batched", False):
+            return False
+        if self._get_frames(**kwargs)[1]:
+            raise NotImplementedError("batched derivative stencils report the body and wind frames; use stab_frame=False")
+        return True
+
     def stability_derivatives(self, **kwargs):
         derivs = {}                                                            # scene.py:1876-1994
         keys, wind = self._frame_keys(**kwargs)
         dtheta = kwargs.get("dtheta", 0.5)
+        batched = self._batched_ok(kwargs)
+        kwargs = {k: v for k, v in kwargs.items() if k != "batched"}
         for name in self._get_aircraft(**kwargs):
             ap = self._airplanes[name]
             alpha_0, beta_0, _ = ap.get_aerodynamic_state()
+            if batched:
+                a_fwd, a_bwd, b_fwd, b_bwd = self._stencil_totals(name, [
+                    lambda a: a.set_aerodynamic_state(alpha=alpha_0 + dtheta),
+                    lambda a: a.set_aerodynamic_state(alpha=alpha_0 - dtheta),
+                    lambda a: a.set_aerodynamic_state(alpha=alpha_0, beta=beta_0 + dtheta),
+                    lambda a: a.set_aerodynamic_state(alpha=alpha_0, beta=beta_0 - dtheta)])
+                scale = 1 / (2 * np.radians(dtheta))
+                d = {}
+                for k in keys:
+                    d[k + ",a"] = (a_fwd[k] - a_bwd[k]) * scale
+                    d[k + ",b"] = (b_fwd[k] - b_bwd[k]) * scale
+                if wind:
+                    d["%_static_margin"] = -d["Cm_w,a"] / d["CL,a"] * 100.0
+                derivs[name] = d
+                continue
             ap.set_aerodynamic_state(alpha=alpha_0 + dtheta)
             a_fwd = self._solve_nd(**kwargs)[name]["total"]
             ap.set_aerodynamic_state(alpha=alpha_0 - dtheta)
@@ -620,6 +672,8 @@ class Scene:
         derivs = {}                                                            # scene.py:1997-2177
         keys, _ = self._frame_keys(**kwargs)
         step = kwargs.get("dtheta_dot", 0.005)
+        batched = self._batched_ok(kwargs)
+        kwargs = {k: v for k, v in kwargs.items() if k != "batched"}
         for name in self._get_aircraft(**kwargs):
             ap = self._airplanes[name]
             _, _, vel_0 = ap.get_aerodynamic_state()
@@ -630,14 +684,20 @@ class Scene:
             elif ap.angular_rate_frame == "wind":
                 perts = [body_to_earth(ap.q_to_wind, p) for p in perts]
             pairs = []
-            for p in perts:
-                ap.w = omega_0 + p
-                fwd = self._solve_nd(**kwargs)[name]["total"]
-                ap.w = omega_0 - p
-                bwd = self._solve_nd(**kwargs)[name]["total"]
-                pairs.append((fwd, bwd))
-            ap.w = omega_0
-            self._solved = False
+            if batched:
+                def rate(dw):
+                    return lambda a: setattr(a, "w", omega_0 + dw)
+                tot = self._stencil_totals(name, [rate(sgn * p) for p in perts for sgn in (1.0, -1.0)])
+                pairs = [(tot[2 * i], tot[2 * i + 1]) for i in range(3)]
+            else:
+                for p in perts:
+                    ap.w = omega_0 + p
+                    fwd = self._solve_nd(**kwargs)[name]["total"]
+                    ap.w = omega_0 - p
+                    bwd = self._solve_nd(**kwargs)[name]["total"]
+                    pairs.append((fwd, bwd))
+                ap.w = omega_0
+                self._solved = False
             _, c, b = self.get_aircraft_reference_geometry(aircraft=name)
             lat, lon = 2 * vel_0 / b, 2 * vel_0 / c
             dx_inv = 1 / (2 * step)

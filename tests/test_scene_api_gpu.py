@@ -56,6 +56,22 @@ def test_derivatives(which):
     _compare(res, GOLD["derivatives"][which], 2e-8 if which in ("damping", "all", "state") else 1e-9)
 
 
+@pytest.mark.parametrize("which", ["stability", "damping", "all"])
+def test_derivatives_batched(which):
+    """The same stencils as ONE batched device pass per aircraft (batched=True): against the reference's answers at the same
+    tolerances, and against the one-solve-at-a-time path."""
+    import copy
+    scene = _scene_cls()(copy.deepcopy(BASE))
+    call = {"stability": scene.stability_derivatives, "damping": scene.damping_derivatives, "all": scene.derivatives}[which]
+    res = call(batched=True)
+    seq = call()
+    _compare(res, seq, 1e-9)
+    if which != "all":      # the golden "all" case also carries the stability frame, which a batch does not report
+        _compare(res, GOLD["derivatives"][which], 2e-8 if which == "damping" else 1e-9)
+    with pytest.raises(NotImplementedError):
+        scene.stability_derivatives(batched=True, stab_frame=True)
+
+
 @pytest.mark.parametrize("which", ["target_CL", "pitch_trim", "pitch_trim_finite_moment", "pitch_trim_orientation", "aero_center", "MAC"])
 def test_other_methods(which):
     res = S.other_case(_scene_cls(), BASE, which)
