@@ -40,23 +40,56 @@ struct RowSmem {
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ Vec3 shfl_v(const Vec3& v, int src) { return Vec3{shfl_d(v.x, src), shfl_d(v.y, src), shfl_d(v.z, src)}; }
 
+#ifndef INF_FAST
+#define INF_FAST 1     // 0: IEEE divisions and FP64-pipe nan_to_num as first written (kept for A/B timing, scripts/influence_bench.py)
+#endif
+
+// 1 / d to about 1 ulp: hardware seed (reciprocal of the high word, ~2^-20) and one cubic Newton step, i.e. 3 FP64-pipe
+// instructions instead of the ~8 plus a guarded slow path of the IEEE division.  Zero, infinity and NaN come out as the seed gives
+// them (inf, 0, NaN), as the division would; the test for that is on the integer pipe.
+__device__ __forceinline__ double rcp_fast(double d) {
+#if INF_FAST
+    double x0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+    const double e = fma(-d, x0, 1.0);
+    const double q = fma(e, e, e);
+    const double r = fma(x0, q, x0);
+    return ((__double2hiint(e) & 0x7ff00000) == 0x7ff00000) ? x0 : r;
+#else
+    return 1.0 / d;
+#endif
+}
+
 // finite vortex segment from a to b seen from the control point (ra = PC - a, rb = PC - b):
 //   (|ra|+|rb|) (ra x rb) / (|ra||rb| (|ra||rb| + ra.rb))          scene.py:525-527, 531-533, 536-538
 __device__ __forceinline__ Vec3 segment_term(const Vec3& ra, double ram, const Vec3& rb, double rbm) {
     const double mm = ram * rbm;
-    const double inv = 1.0 / (mm * (mm + dot(ra, rb)));
+    const double inv = rcp_fast(mm * (mm + dot(ra, rb)));
     return ((ram + rbm) * inv) * cross(ra, rb);
 }
 
 // nan_to_num of the reference (scene.py:624, 630): NaN -> 0, +-inf -> +-DBL_MAX
-__device__ __forceinline__ double nan_to_num(double v) { return (v != v) ? 0.0 : fmin(fmax(v, -DBL_MAX), DBL_MAX); }
+__device__ __forceinline__ double nan_to_num(double v) {
+#if INF_FAST
+    if ((__double2hiint(v) & 0x7ff00000) != 0x7ff00000) return v;      // finite: integer pipe only
+#endif
+    return (v != v) ? 0.0 : fmin(fmax(v, -DBL_MAX), DBL_MAX);
+}
 
 // semi-infinite trailing leg from the joint along u; sign = -1 for the inbound leg, +1 for the outbound leg
-__device__ __forceinline__ Vec3 trailing_term(const Vec3& u, const Vec3& rj, double rjm, double sign, double thr, bool& imp) {
+// `guard` = max(impingement threshold, 1e-13): one comparison settles both tests of the reference for every ordinary pair
+__device__ __forceinline__ Vec3 trailing_term(const Vec3& u, const Vec3& rj, double rjm, double sign, double thr, double guard, bool& imp) {
     const double d = rjm * (rjm - dot(u, rj));                                  // scene.py:621, 627
+#if INF_FAST
+    if (!(d >= guard)) {
+        imp |= (fabs(d) < thr);
+        if (!(d > 1e-13)) return Vec3{0.0, 0.0, 0.0};
+    }
+#else
     imp |= (fabs(d) < thr);
     if (!(d > 1e-13)) return Vec3{0.0, 0.0, 0.0};
-    const double t = sign / d;
+#endif
+    const double t = sign * rcp_fast(d);
     const Vec3 c = cross(u, rj);
     return Vec3{nan_to_num(c.x * t), nan_to_num(c.y * t), nan_to_num(c.z * t)};
 }
@@ -150,6 +183,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
                      ac[(size_t)ac_j * LLS_AC_STRIDE + LLS_AC_POS + 2]};
 
     bool imp = false;
+    const double guard = fmax(thr, 1e-13);
     const double inv4pi = 0.25 / 3.14159265358979323846;
 
     for (int r = 0; r < nrows; ++r) {
@@ -219,15 +253,15 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
             }
         }
 
-        // vectors from the four corners to the control point (airplane.py:672-675, scene.py:501-504);
-        // dp is exactly zero inside one aircraft, so same-aircraft differences keep every digit
-        const Vec3 dp{rs.pos[0][r] - pos_j.x, rs.pos[1][r] - pos_j.y, rs.pos[2][r] - pos_j.z};
-        const Vec3 r0 = (pc - n0) + dp, r1 = (pc - n1) + dp, r0j = (pc - q0) + dp, r1j = (pc - q1) + dp;
+        // vectors from the four corners to the control point (airplane.py:672-675, scene.py:501-504); the offset between the
+        // two aircraft origins is exactly zero inside one aircraft, so same-aircraft differences keep every digit
+        const Vec3 pcs{pc.x + (rs.pos[0][r] - pos_j.x), pc.y + (rs.pos[1][r] - pos_j.y), pc.z + (rs.pos[2][r] - pos_j.z)};
+        const Vec3 r0 = pcs - n0, r1 = pcs - n1, r0j = pcs - q0, r1j = pcs - q1;
         const double r0m = norm(r0), r1m = norm(r1), r0jm = norm(r0j), r1jm = norm(r1j);
 
         Vec3 v = segment_term(r0j, r0jm, r0, r0m) + segment_term(r1, r1m, r1j, r1jm);   // joints, scene.py:531-538
         if (i != j_raw) v = v + segment_term(r0, r0m, r1, r1m);                       // bound, zero on the diagonal (scene.py:528)
-        v = v + trailing_term(u0, r0j, r0jm, -1.0, thr, imp) + trailing_term(u1, r1j, r1jm, 1.0, thr, imp);
+        v = v + trailing_term(u0, r0j, r0jm, -1.0, thr, guard, imp) + trailing_term(u1, r1j, r1jm, 1.0, thr, guard, imp);
         if (!j_real) v = Vec3{0.0, 0.0, 0.0};
         if (writes) {
             double* row = V + (size_t)(lrow0 + r) * 3 * ld + j_raw;
