@@ -438,12 +438,47 @@ class Scene:
         if self._num_aircraft == 0:
             raise RuntimeError("There are no aircraft in this scene. No calculations can be performed.")
         name = self._only_aircraft(aircraft)
-        ap = self._airplanes[name]
         if self._current_pose_key() != self._pose_key:
             self._perform_geometry_and_atmos_calcs()
+        return self._solve_batch_rows(self._batch_rows(name, states), max_batch)
+
+    def _batch_rows(self, name, states):
+        """(ncases, n_aircraft, AC_STRIDE) state blocks of a list of state dictionaries for airplane ``name``.  Plain
+        {"position", "velocity": float, "alpha", "beta"} states (an alpha / beta / airspeed sweep, BASELINE.json configs[2]) are
+        converted in one vectorised pass with the formulas of Airplane.set_state / set_aerodynamic_state; anything else goes
+        through the airplane object one state at a time."""
+        ap = self._airplanes[name]
+        ia = [a.name for a in self._airplane_objects].index(name)
+        pose = (np.array(ap.p_bar, dtype=float), np.array(ap.q, dtype=float))
+        plain = {"position", "velocity", "alpha", "beta"}
+        if len(states) > 0 and all(set(st) <= plain and isinstance(st.get("velocity"), float)
+                                   and isinstance(st.get("alpha", 0.0), (int, float)) and isinstance(st.get("beta", 0.0), (int, float))
+                                   and isinstance(st.get("position", [0.0, 0.0, 0.0]), (list, tuple))
+                                   and all(isinstance(x, (int, float)) for x in st.get("position", [0.0, 0.0, 0.0]))
+                                   for st in states):
+            pos = np.array([st.get("position", [0.0, 0.0, 0.0]) for st in states], dtype=float)
+            if not (pos == pose[0][np.newaxis, :]).all() or not np.allclose(pose[1], [1.0, 0.0, 0.0, 0.0], rtol=0, atol=1e-15):
+                # set_state without an "orientation" key resets it to level flight: only then is the pose kept
+                raise ValueError("solve_forces_batch: every state must keep the scene's current position and orientation")
+            alpha = np.radians(np.array([st.get("alpha", 0.0) for st in states], dtype=float))
+            beta = np.radians(np.array([st.get("beta", 0.0) for st in states], dtype=float))
+            speed = np.array([st["velocity"] for st in states], dtype=float)
+            C_a, S_a = np.cos(alpha), np.sin(alpha)                       # Airplane.set_aerodynamic_state
+            flank = np.arctan(np.tan(beta) / C_a)
+            C_B, S_B = np.cos(flank), np.sin(flank)
+            scale = 1.0 / np.sqrt(1.0 - S_a * S_a * S_B * S_B)
+            v_body = np.stack([speed * C_a * C_B * scale, speed * C_a * S_B * scale, speed * S_a * C_B * scale], axis=1)
+            wind = np.asarray(self._get_wind(pose[0]), dtype=float)
+            saved = ap.get_state()
+            try:
+                ap.w = np.zeros(3)                                        # no "angular_rates" key: zero
+                rows = np.repeat(build_aircraft_state(self)[np.newaxis], len(states), axis=0)
+            finally:
+                ap.v, ap.w, ap.p_bar, ap.q = saved
+            rows[:, ia, L.AC_VTRANS:L.AC_VTRANS + 3] = -(wind[np.newaxis, :] + v_body)     # level flight: earth axes = body axes
+            return rows
         saved = ap.get_state()
         saved_frame = ap.angular_rate_frame
-        pose = (np.array(ap.p_bar, dtype=float), np.array(ap.q, dtype=float))
         rows = []
         try:
             for st in states:
@@ -455,7 +490,7 @@ class Scene:
         finally:
             ap.v, ap.w, ap.p_bar, ap.q = saved
             ap.angular_rate_frame = saved_frame
-        return self._solve_batch_rows(np.array(rows), max_batch)
+        return np.array(rows)
 
     def _solve_batch_rows(self, ac_states, max_batch=4096):
         """Device part of a batch: ``ac_states`` (ncases, n_aircraft, AC_STRIDE) per-aircraft state blocks as build_aircraft_state

@@ -158,3 +158,23 @@ def test_unsupported_airfoil_types_fail_loudly():
     d["scene"]["aircraft"]["test_plane"]["file"]["airfoils"]["NACA_0010"] = {"type": "database", "input_file": "x.txt"}
     with pytest.raises(NotImplementedError):
         Scene(d)
+
+
+# ---- batches: state blocks of a sweep (BASELINE.json configs[2]) ----------------------------------------------------------
+def test_sweep_state_blocks_vectorised_equal_per_state():
+    """A plain alpha / beta / airspeed sweep is converted to per-case state blocks in one vectorised pass; the blocks must equal
+    what Airplane.set_state produces one state at a time (the path every other kind of state takes)."""
+    scene = _scene(state={"position": [0.0, 0.0, 0.0], "velocity": 100.0, "alpha": 2.0})
+    name = "test_plane"
+    rng = np.random.default_rng(3)
+    plain = [{"position": [0.0, 0.0, 0.0], "velocity": float(v), "alpha": float(a), "beta": float(b)}
+             for v, a, b in zip(rng.uniform(50, 200, 64), rng.uniform(-10, 15, 64), rng.uniform(-12, 12, 64))]
+    fast = scene._batch_rows(name, plain)
+    # the same states in a form the vectorised pass does not take (an explicit zero rate vector)
+    slow = scene._batch_rows(name, [dict(st, angular_rates=[0.0, 0.0, 0.0]) for st in plain])
+    assert fast.shape == slow.shape == (64, 1, slow.shape[2])
+    assert np.abs(fast - slow).max() <= 1e-13 * np.abs(slow).max()
+    # the airplane is left as it was
+    assert abs(scene._airplanes[name].get_aerodynamic_state()[0] - 2.0) < 1e-12
+    with pytest.raises(ValueError):
+        scene._batch_rows(name, [{"position": [1.0, 0.0, 0.0], "velocity": 100.0, "alpha": 1.0}])
