@@ -144,3 +144,54 @@ def test_c2_traditional_4000_control_points():
         assert abs(FM[name]["total"][key] - ref_total[key]) <= RTOL * abs(ref_total[key]), key
     # the numbers SURVEY.md section 6 recorded for this configuration
     assert abs(ref_total["CL"] - 0.36518657437915686) < 1e-12 and abs(ref_total["CD"] - 0.014902688270872865) < 1e-12
+
+
+def test_c2_full_size_properties():
+    """Size-independent properties at BASELINE.json configs[1]'s full size (N = 4000), next to the golden comparison above:
+    (1) repeatability: every kernel reduces in a fixed order, so a second solve returns the same bits;
+    (2) similarity: with linear airfoils (no Reynolds / Mach terms) the lifting-line equations are homogeneous in the
+        freestream, so doubling the velocity and the angular rates doubles the circulation (linear and converged) and
+        quadruples every force and moment (the residual quadruples too and the stopping test is absolute, so the
+        Newton count may grow by one);
+    (3) mirror symmetry: the aeroplane flies without sideslip, so the left and right halves of the main wing and of the
+        horizontal tail carry the same lift and drag and opposite side force."""
+    from machupx_b200 import layout as L
+    from machupx_b200.device import DeviceScene
+    tables, ac_state, g, meta = load("c2_traditional_n4000")
+    sp = meta["solver"]
+
+    def solve(state):
+        dev = DeviceScene(tables)
+        dev.upload_state(state)
+        dev.flow_state()
+        dev.build_influence(1e-10)
+        dev.solve_linear()
+        glin = dev.gamma()
+        it, err, status, hist = dev.solve_nonlinear(sp["convergence"], sp["relaxation"], sp["max_iterations"])
+        return glin, dev.gamma(), it, dev.integrate()
+
+    glin1, gam1, it1, fm1 = solve(ac_state)
+    glin1b, gam1b, it1b, fm1b = solve(ac_state)
+    assert it1 == it1b and np.array_equal(gam1, gam1b) and np.array_equal(glin1, glin1b) and np.array_equal(fm1, fm1b)
+
+    fast = np.array(ac_state, dtype=float)
+    fast[:, L.AC_VTRANS:L.AC_VTRANS + 3] *= 2.0
+    fast[:, L.AC_W:L.AC_W + 3] *= 2.0
+    glin2, gam2, it2, fm2 = solve(fast)
+    assert it1 <= it2 <= it1 + 1
+    assert np.abs(glin2 - 2.0 * glin1).max() <= 1e-12 * np.abs(glin2).max()
+    # the converged circulation is only as homogeneous as the stopping test |R| <= 1e-10 (an absolute tolerance) lets it be
+    assert np.abs(gam2 - 2.0 * gam1).max() <= 1e-9 * np.abs(gam2).max()
+    assert np.abs(fm2 - 4.0 * fm1).max() <= 1e-9 * np.abs(fm2).max()
+
+    names = meta["aircraft"][0]["segments"]
+    for wing in ("main_wing", "h_stab"):
+        pair = [i for i, nme in enumerate(names) if nme.startswith(wing)]
+        if len(pair) != 2:
+            continue
+        a, b = fm1[pair[0]], fm1[pair[1]]          # 12 sums per segment: inviscid F, M, viscous F, M (earth axes)
+        scale = np.abs(fm1).max()
+        for comp in (0, 2, 6, 8):                  # x and z force components: equal
+            assert abs(a[comp] - b[comp]) <= 1e-9 * scale, (wing, comp)
+        for comp in (1, 7):                        # side force: opposite
+            assert abs(a[comp] + b[comp]) <= 1e-9 * scale, (wing, comp)
