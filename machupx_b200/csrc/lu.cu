@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
                                                                 double* __restrict__ scalars, int* __restrict__ status, CaseStrides cs,
                                                                 int* __restrict__ counters, int chunk, int nworkers, int* __restrict__ diag_sm,
-                                                                int* __restrict__ claims, int panel_sms) {
+                                                                int* __restrict__ claims, int panel_sms, int inv_block) {
     constexpr int NT = WORKERS ? 256 : LU_THREADS;   // threads per CTA; the panel roles always run on threads 0..127
     static_assert(!(WORKERS && (FIRST || PASSES != 1)), "workers take one panel per visit");
     // programmatic dependent launch: the CTAs of block step k+1 are placed on the SMs while step k drains and start the moment
@@ -608,8 +608,13 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         pb = s_role;
     }
     int bi, bj;
-    enum { DIAG, LCOL, UROW, OTHER } role;
-    if (pb == 0) {
+    // INV (block `inv_block` = 2 rem - 1, right behind the panel tiles, if there is one): inverts U11 for the back-substitution chain.  It waits for
+    // the diagonal block like a panel CTA and runs beside them; with the inversion inside the diag CTA that CTA was the last
+    // of a chain-bound launch to finish (by 5-16 k cycles for trailing matrices of 24-46 block rows).
+    enum { DIAG, LCOL, UROW, OTHER, INV } role;
+    if (inv_block >= 0 && pb == inv_block) {
+        role = INV; bi = base; bj = base;
+    } else if (pb == 0) {
         role = DIAG; bi = base; bj = base;
     } else if (pb < rem) {
         role = LCOL; bi = base + pb; bj = base;
@@ -617,13 +622,15 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         role = UROW; bi = base; bj = base + (pb - rem + 1);
     } else {
         role = OTHER;
-        const int o = pb - (2 * rem - 1);
+        const int o = pb - (2 * rem - 1) - (inv_block >= 0 ? 1 : 0);
         bi = base + 1 + o / (rem - 1);
         bj = base + 1 + o % (rem - 1);
     }
     double* gC = M + (size_t)bi * NB * ld + (size_t)bj * NB;
     LU_CLK(0);
-    if (!FIRST) {
+    if (role == INV) {
+        // no tile of its own
+    } else if (!FIRST) {
         double acc[4][WarpTile<NT>::NI][2];
         {
             double2 cn[4][WarpTile<NT>::NI];
@@ -716,7 +723,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
             scalars[1] = (blk == 0) ? m : fmin(m, scalars[1]);
         }
         if (rhs != nullptr && t < 32) forward_rhs_warp(sC, rhs + (size_t)blk * NB);
-        // W = U11, pre-scaled rows in sA: the solve below turns the identity into inv(U11)
+        // W = U11, pre-scaled rows in sA: the solve below turns the identity into inv(U11) (unless an INV CTA does that)
     } else {
         // panel roles: wait for the factored diagonal block
         if (t == 0) {
@@ -734,12 +741,13 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         // LCOL: W = U11 (scaled upper part, row-major); UROW (transposed problem): W = L11^T, W(p, c) = image[c][p]
         panel_sync<NT>();
     }
-    {
+    const bool solves = !(role == DIAG && inv_block >= 0);
+    if (solves) {
         // 2-D cyclic register tile: a[i][j] <-> (row ty + 16 i, col tx + 8 j) of X; UROW works on the transposed tile
         const int ty = t >> 3, tx = t & 7;
         const int sr = (role == UROW) ? 1 : TS, sc = (role == UROW) ? TS : 1;
         double a[4][8];
-        if (role == DIAG) {
+        if (role == DIAG || role == INV) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -761,8 +769,10 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
             for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
     }
     panel_sync<NT>();
-    if (role == DIAG) store_tile(uinv + (size_t)blk * NB * NB, NB, sC);
-    else store_tile(gC, ld, sC);
+    if (solves) {
+        if (role == DIAG || role == INV) store_tile(uinv + (size_t)blk * NB * NB, NB, sC);
+        else store_tile(gC, ld, sC);
+    }
     LU_CLK(8);
     }   // panel roles
     if (WORKERS && rem > 1) {
@@ -1135,6 +1145,7 @@ static bool g_chain_guard = true;     // LLS_LU_CHAIN_GUARD=0: update CTAs do no
 static int g_worker_reserve = 48;     // LLS_LU_WORKER_RESERVE: CTA slots left to the panel tiles at the start of a launch
 
 static int g_pack_min_rem = 0;        // LLS_LU_PACK_MIN_REM: trailing matrices of at least this many block rows claim roles by SM (0 = never, the default: the claim at CTA start costs more than the isolation returns, 2.83 -> 2.95 ms at N = 4000)
+static bool g_lu_inv_cta = true;      // LLS_LU_INV_CTA=0: the diag CTA inverts U11 itself after publishing
 static bool g_lu_pdl = true;          // LLS_LU_PDL=0: plain stream-ordered launches of the block steps
 
 template <class... KArgs, class... Args>
@@ -1162,6 +1173,8 @@ static int lu_prepare(Scene* s) {
         if (env != nullptr && atoi(env) >= 1) g_worker_chunk = atoi(env);
         env = getenv("LLS_LU_PACK_MIN_REM");
         if (env != nullptr) g_pack_min_rem = atoi(env);
+        env = getenv("LLS_LU_INV_CTA");
+        if (env != nullptr && env[0] == '0') g_lu_inv_cta = false;
         env = getenv("LLS_LU_PDL");
         if (env != nullptr && env[0] == '0') g_lu_pdl = false;
         env = getenv("LLS_LU_CHAIN_GUARD");
@@ -1209,10 +1222,13 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     int* diag_sm = g_chain_guard ? s->lu_flags + 3 * (nblk + 1) : nullptr;   // where the diag CTA announces its SM
     int* claims = s->lu_flags + 4 * (nblk + 1);     // two role-claim counters per block step (zeroed by the first launch)
     const bool workers_ok = (ncases == 1) && g_worker_min_rem > 0;
+    const int inv_cta = g_lu_inv_cta ? 1 : 0;      // one more CTA per launch inverts U11 (see the INV role)
     {
         const int rem = nblk;       // block 0 and its panel
-        LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false>, dim3(2 * rem - 1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0));
+        const int grid = 2 * rem - 1;
+        LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false>, dim3(grid + inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
+                inv_cta ? grid : -1));
         count_launch();
     }
     for (int k = 0; k + 1 < nblk;) {
@@ -1225,7 +1241,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             if (nworkers > chunks) nworkers = chunks;
             if (nworkers < 1) nworkers = 1;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, true>, dim3(2 * rem - 1 + (int)nworkers, 1, 1), 256, (size_t)3 * TILE_BYTES, st,
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8), (int)nworkers, diag_sm, nullptr, 0));
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8), (int)nworkers, diag_sm, nullptr, 0, -1));
             count_launch();
             k += 1;
             continue;
@@ -1234,20 +1250,25 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
         // 123 -> 113 ms, N = 8000 17.1 -> 16.5 ms, N = 4000 3.25 -> 3.33 ms when pairing everything)
         if (rem >= LU_PAIR_MIN_REM && g_lu_pairs) {
             // thin launch: block row / column k+1 only (update with panel k, factor panel k+1) ...
-            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(2 * rem - 1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0));
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(2 * rem - 1 + inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0,
+                inv_cta ? 2 * rem - 1 : -1));
             count_launch();
             // ... then one visit of the rest with panels k and k+1 together, factoring panel k+2 on the way
             const int rem2 = rem - 1;
             const int psm2 = (g_pack_min_rem > 0 && rem2 >= g_pack_min_rem) ? (2 * rem2 - 2 + 2) / 3 : 0;
-            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 2, false>, dim3(rem2 * rem2, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm2 ? claims : nullptr, psm2));
+            const int inv2 = psm2 ? 0 : inv_cta;
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 2, false>, dim3(rem2 * rem2 + inv2, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm2 ? claims : nullptr, psm2,
+                inv2 ? 2 * rem2 - 1 : -1));
             count_launch();
             k += 2;
         } else {
             const int psm = (g_pack_min_rem > 0 && rem >= g_pack_min_rem) ? (2 * rem - 2 + 2) / 3 : 0;
-            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(rem * rem, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm ? claims : nullptr, psm));
+            const int inv1 = psm ? 0 : inv_cta;
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(rem * rem + inv1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm ? claims : nullptr, psm,
+                inv1 ? 2 * rem - 1 : -1));
             count_launch();
             k += 1;
         }
