@@ -298,8 +298,9 @@ __device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine&
 //   U12^T = C^T (L11^T)^-1      (W = L11^T, unit diagonal: W(p, c) = L11(c, p) = image[c][p]; wr = 1, wc = TS; dinv = 1;
 //                                the tile is loaded / stored transposed)
 //   inv(U11) = I U11^-1         (tile = identity), used by the back-substitution chain.
-template <int J, bool TR>
-__device__ __forceinline__ void panel_group(double (&a)[4][8], const double* __restrict__ sW, const double* __restrict__ dinv,
+// RI = register rows per thread: 4 for a whole tile, 2 when two CTAs share a panel tile (each solves 32 of the 64 independent rows)
+template <int J, bool TR, int RI>
+__device__ __forceinline__ void panel_group(double (&a)[RI][8], const double* __restrict__ sW, const double* __restrict__ dinv,
                                             int tx, int lane) {
     constexpr int wr = TR ? 1 : TS, wc = TR ? TS : 1;
 #pragma unroll 1
@@ -312,29 +313,29 @@ __device__ __forceinline__ void panel_group(double (&a)[4][8], const double* __r
 #pragma unroll
         for (int j = J + 1; j < 8; ++j) w[j] = wrow[8 * j * wc];
         const double rp = TR ? 1.0 : dinv[p];
-        double ap[4];
+        double ap[RI];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ap[i] = __shfl_sync(0xffffffffu, a[i][J], src);
+        for (int i = 0; i < RI; ++i) ap[i] = __shfl_sync(0xffffffffu, a[i][J], src);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i][J] = (tx == pp) ? ap[i] * rp : fma(-ap[i], w[J], a[i][J]);
+        for (int i = 0; i < RI; ++i) a[i][J] = (tx == pp) ? ap[i] * rp : fma(-ap[i], w[J], a[i][J]);
 #pragma unroll
         for (int j = J + 1; j < 8; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i][j] = fma(-ap[i], w[j], a[i][j]);
+            for (int i = 0; i < RI; ++i) a[i][j] = fma(-ap[i], w[j], a[i][j]);
     }
 }
 
-template <bool TR>
-__device__ __forceinline__ void panel_solve(double (&a)[4][8], const double* __restrict__ sW, const double* __restrict__ dinv) {
+template <bool TR, int RI = 4>
+__device__ __forceinline__ void panel_solve(double (&a)[RI][8], const double* __restrict__ sW, const double* __restrict__ dinv) {
     const int tx = threadIdx.x & 7, lane = threadIdx.x & 31;
-    panel_group<0, TR>(a, sW, dinv, tx, lane);
-    panel_group<1, TR>(a, sW, dinv, tx, lane);
-    panel_group<2, TR>(a, sW, dinv, tx, lane);
-    panel_group<3, TR>(a, sW, dinv, tx, lane);
-    panel_group<4, TR>(a, sW, dinv, tx, lane);
-    panel_group<5, TR>(a, sW, dinv, tx, lane);
-    panel_group<6, TR>(a, sW, dinv, tx, lane);
-    panel_group<7, TR>(a, sW, dinv, tx, lane);
+    panel_group<0, TR, RI>(a, sW, dinv, tx, lane);
+    panel_group<1, TR, RI>(a, sW, dinv, tx, lane);
+    panel_group<2, TR, RI>(a, sW, dinv, tx, lane);
+    panel_group<3, TR, RI>(a, sW, dinv, tx, lane);
+    panel_group<4, TR, RI>(a, sW, dinv, tx, lane);
+    panel_group<5, TR, RI>(a, sW, dinv, tx, lane);
+    panel_group<6, TR, RI>(a, sW, dinv, tx, lane);
+    panel_group<7, TR, RI>(a, sW, dinv, tx, lane);
 }
 
 // y = L^-1 b for the unit-lower factor held row-major in sC; warp 0 only, lane l keeps b[l] and b[l + 32]
@@ -516,7 +517,7 @@ __device__ __forceinline__ void lu_update_worker(const UpdateGeom& G, int* __res
 // WORKERS: the tiles without a panel role are not mapped to CTAs; blocks >= 2 rem - 1 are persistent workers (and the panel
 // CTAs turn into workers when their panel is done), see lu_update_worker.  `counters` holds one work counter per block step,
 // zeroed by the FIRST launch of every factorisation.
-template <bool FIRST, int PASSES, bool WORKERS>
+template <bool FIRST, int PASSES, bool WORKERS, bool SPLIT = false>
 __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) lu_step_kernel(double* __restrict__ M, int ld, int k, int rem,
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
@@ -525,6 +526,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
                                                                 int* __restrict__ claims, int panel_sms, int inv_block) {
     constexpr int NT = WORKERS ? 256 : LU_THREADS;   // threads per CTA; the panel roles always run on threads 0..127
     static_assert(!(WORKERS && (FIRST || PASSES != 1)), "workers take one panel per visit");
+    static_assert(!(SPLIT && (WORKERS || PASSES != 1)), "split panel tiles belong to the chain-bound launches");
     // programmatic dependent launch: the CTAs of block step k+1 are placed on the SMs while step k drains and start the moment
     // its memory is visible, instead of paying the launch latency between two launches of the chain (no-ops in a plain launch)
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -612,17 +614,27 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
     // the diagonal block like a panel CTA and runs beside them; with the inversion inside the diag CTA that CTA was the last
     // of a chain-bound launch to finish (by 5-16 k cycles for trailing matrices of 24-46 block rows).
     enum { DIAG, LCOL, UROW, OTHER, INV } role;
-    if (inv_block >= 0 && pb == inv_block) {
-        role = INV; bi = base; bj = base;
+    // SPLIT: two CTAs per panel tile (and two for the inverse).  Both update the whole tile (the tensor work is not on anybody's
+    // critical path here), then each solves 32 of its 64 independent rows (L tiles, inverse) or columns (U tiles): half the FMAs
+    // and shuffles per pivot of the issue-bound substitution.  Used while launches are chain-bound and SMs are idle anyway.
+    int half = 0;
+    const int npanel = SPLIT ? 4 * (rem - 1) : 2 * (rem - 1);
+    const int ninv = (inv_block >= 0) ? (SPLIT ? 2 : 1) : 0;
+    if (inv_block >= 0 && pb >= inv_block && pb < inv_block + ninv) {
+        role = INV; bi = base; bj = base; half = pb - inv_block;
     } else if (pb == 0) {
         role = DIAG; bi = base; bj = base;
-    } else if (pb < rem) {
-        role = LCOL; bi = base + pb; bj = base;
-    } else if (pb < 2 * rem - 1) {
-        role = UROW; bi = base; bj = base + (pb - rem + 1);
+    } else if (pb <= npanel / 2) {
+        const int q = SPLIT ? (pb - 1) >> 1 : pb - 1;
+        half = SPLIT ? (pb - 1) & 1 : 0;
+        role = LCOL; bi = base + 1 + q; bj = base;
+    } else if (pb <= npanel) {
+        const int q = SPLIT ? (pb - 1 - npanel / 2) >> 1 : pb - 1 - npanel / 2;
+        half = SPLIT ? (pb - 1 - npanel / 2) & 1 : 0;
+        role = UROW; bi = base; bj = base + 1 + q;
     } else {
         role = OTHER;
-        const int o = pb - (2 * rem - 1) - (inv_block >= 0 ? 1 : 0);
+        const int o = pb - (npanel + 1) - ninv;
         bi = base + 1 + o / (rem - 1);
         bj = base + 1 + o % (rem - 1);
     }
@@ -657,7 +669,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
             acc_io<false, NT>(acc, gC, ld);                                       // C - L U
             return;
         }
-        if (rhs != nullptr && bj == base && t < NB) {   // b[bi] -= L[bi,kk] y_kk for the last panel applied (the thin launch did the other)
+        if (rhs != nullptr && bj == base && half == 0 && t < NB) {   // b[bi] -= L[bi,kk] y_kk for the last panel applied (the thin launch did the other)
             double s = 0.0;
             const double* yk = rhs + (size_t)(k + PASSES - 1) * NB;
 #pragma unroll 8
@@ -742,10 +754,11 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         panel_sync<NT>();
     }
     const bool solves = !(role == DIAG && inv_block >= 0);
-    if (solves) {
-        // 2-D cyclic register tile: a[i][j] <-> (row ty + 16 i, col tx + 8 j) of X; UROW works on the transposed tile
-        const int ty = t >> 3, tx = t & 7;
-        const int sr = (role == UROW) ? 1 : TS, sc = (role == UROW) ? TS : 1;
+    const bool whole = !SPLIT || role == DIAG;
+    const int ty = t >> 3, tx = t & 7;
+    // 2-D cyclic register tile: a[i][j] <-> (row ty + 16 i, col tx + 8 j) of X; UROW works on the transposed tile
+    const int sr = (role == UROW) ? 1 : TS, sc = (role == UROW) ? TS : 1;
+    if (solves && whole) {
         double a[4][8];
         if (role == DIAG || role == INV) {
 #pragma unroll
@@ -767,11 +780,42 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
+    } else if (solves) {
+        // this CTA's half: rows (L tile, inverse) / columns (U tile) 32 half .. 32 half + 31, i.e. register rows 2 half, 2 half + 1
+        double a[2][8];
+        const int r0 = ty + 32 * half;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                a[i][j] = (role == INV) ? ((r0 + 16 * i == tx + 8 * j) ? 1.0 : 0.0) : sC[(r0 + 16 * i) * sr + (tx + 8 * j) * sc];
+        LU_CLK(6);
+        if (role == UROW) panel_solve<true, 2>(a, sA, dinv);
+        else panel_solve<false, 2>(a, sA, dinv);
+        LU_CLK(7);
+        panel_sync<NT>();
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sC[(r0 + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
     }
     panel_sync<NT>();
     if (solves) {
-        if (role == DIAG || role == INV) store_tile(uinv + (size_t)blk * NB * NB, NB, sC);
-        else store_tile(gC, ld, sC);
+        double* dst = (role == DIAG || role == INV) ? uinv + (size_t)blk * NB * NB : gC;
+        const size_t ldd = (role == DIAG || role == INV) ? (size_t)NB : (size_t)ld;
+        if (whole) {
+            store_tile(dst, ldd, sC);
+        } else if (role != UROW) {      // rows 32 half .. +31, all 64 columns: 32 x 32 double2
+            const int c2 = t & 31, rr = t >> 5;
+#pragma unroll 4
+            for (int r = 32 * half + rr; r < 32 * half + 32; r += 4)
+                *reinterpret_cast<double2*>(dst + (size_t)r * ldd + 2 * c2) = *reinterpret_cast<const double2*>(sC + r * TS + 2 * c2);
+        } else {                        // all 64 rows, columns 32 half .. +31: 64 x 16 double2
+            const int c2 = t & 15, rr = t >> 4;
+#pragma unroll 4
+            for (int r = rr; r < NB; r += 8)
+                *reinterpret_cast<double2*>(dst + (size_t)r * ldd + 32 * half + 2 * c2) = *reinterpret_cast<const double2*>(sC + r * TS + 32 * half + 2 * c2);
+        }
     }
     LU_CLK(8);
     }   // panel roles
@@ -1145,6 +1189,7 @@ static bool g_chain_guard = true;     // LLS_LU_CHAIN_GUARD=0: update CTAs do no
 static int g_worker_reserve = 48;     // LLS_LU_WORKER_RESERVE: CTA slots left to the panel tiles at the start of a launch
 
 static int g_pack_min_rem = 0;        // LLS_LU_PACK_MIN_REM: trailing matrices of at least this many block rows claim roles by SM (0 = never, the default: the claim at CTA start costs more than the isolation returns, 2.83 -> 2.95 ms at N = 4000)
+static int g_split_max_rem = 36;      // LLS_LU_SPLIT_MAX_REM: trailing matrices of at most this many block rows use two CTAs per panel tile (0 = never)
 static bool g_lu_inv_cta = true;      // LLS_LU_INV_CTA=0: the diag CTA inverts U11 itself after publishing
 static bool g_lu_pdl = true;          // LLS_LU_PDL=0: plain stream-ordered launches of the block steps
 
@@ -1173,6 +1218,8 @@ static int lu_prepare(Scene* s) {
         if (env != nullptr && atoi(env) >= 1) g_worker_chunk = atoi(env);
         env = getenv("LLS_LU_PACK_MIN_REM");
         if (env != nullptr) g_pack_min_rem = atoi(env);
+        env = getenv("LLS_LU_SPLIT_MAX_REM");
+        if (env != nullptr) g_split_max_rem = atoi(env);
         env = getenv("LLS_LU_INV_CTA");
         if (env != nullptr && env[0] == '0') g_lu_inv_cta = false;
         env = getenv("LLS_LU_PDL");
@@ -1190,6 +1237,8 @@ static int lu_prepare(Scene* s) {
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         g_attr_done = true;
     }
     (void)s;
@@ -1223,12 +1272,20 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     int* claims = s->lu_flags + 4 * (nblk + 1);     // two role-claim counters per block step (zeroed by the first launch)
     const bool workers_ok = (ncases == 1) && g_worker_min_rem > 0;
     const int inv_cta = g_lu_inv_cta ? 1 : 0;      // one more CTA per launch inverts U11 (see the INV role)
+    const bool split_ok = (ncases == 1);           // a batch hides the chain of one case behind the other cases: no redundant tile updates there
     {
         const int rem = nblk;       // block 0 and its panel
-        const int grid = 2 * rem - 1;
-        LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false>, dim3(grid + inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
-                M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
-                inv_cta ? grid : -1));
+        if (split_ok && rem <= g_split_max_rem) {
+            const int roles = 1 + 4 * (rem - 1);
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false, true>, dim3(roles + 2 * inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                    M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
+                    inv_cta ? roles : -1));
+        } else {
+            const int grid = 2 * rem - 1;
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false>, dim3(grid + inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                    M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
+                    inv_cta ? grid : -1));
+        }
         count_launch();
     }
     for (int k = 0; k + 1 < nblk;) {
@@ -1265,6 +1322,15 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             k += 2;
         } else {
             const int psm = (g_pack_min_rem > 0 && rem >= g_pack_min_rem) ? (2 * rem - 2 + 2) / 3 : 0;
+            if (split_ok && !psm && rem <= g_split_max_rem) {     // chain-bound regime: two CTAs per panel tile and for the inverse
+                const int roles = 1 + 4 * (rem - 1);
+                LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false, true>, dim3(roles + 2 * inv_cta + (rem - 1) * (rem - 1), 1, ncases), LU_THREADS,
+                    (size_t)2 * TILE_BYTES, st, M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm,
+                    nullptr, 0, inv_cta ? roles : -1));
+                count_launch();
+                k += 1;
+                continue;
+            }
             const int inv1 = psm ? 0 : inv_cta;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(rem * rem + inv1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                 M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm ? claims : nullptr, psm,

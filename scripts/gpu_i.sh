@@ -3,12 +3,11 @@ set -u
 mkdir -p gpurun_out
 rm -f gpurun_out/i_lu.jsonl gpurun_out/i_lu.err
 run() { echo "# $*" >> gpurun_out/i_lu.jsonl; env "$@" timeout 120 python scripts/lu_bench.py $N 5 >> gpurun_out/i_lu.jsonl 2>> gpurun_out/i_lu.err; }
-for N in 64 130 200 1000 2000 4000 8000; do
+for N in 64 200 1000 2000 4000 8000; do
 run LLS_LU_SPLIT_MAX_REM=0
 run LLS_LU_SPLIT_MAX_REM=24
 run LLS_LU_SPLIT_MAX_REM=36
 run LLS_LU_SPLIT_MAX_REM=48
 done
 cat gpurun_out/i_lu.jsonl; tail -5 gpurun_out/i_lu.err
-timeout 120 python scripts/lu_clocks.py 4000 > gpurun_out/i_clocks_split.txt 2>&1; sed -n '30p;40p;55p' gpurun_out/i_clocks_split.txt | cut -c1-230
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
