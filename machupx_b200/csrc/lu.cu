@@ -517,7 +517,7 @@ __device__ __forceinline__ void lu_update_worker(const UpdateGeom& G, int* __res
 // WORKERS: the tiles without a panel role are not mapped to CTAs; blocks >= 2 rem - 1 are persistent workers (and the panel
 // CTAs turn into workers when their panel is done), see lu_update_worker.  `counters` holds one work counter per block step,
 // zeroed by the FIRST launch of every factorisation.
-template <bool FIRST, int PASSES, bool WORKERS, bool SPLIT = false>
+template <bool FIRST, int PASSES, bool WORKERS, int SPLIT = 1>
 __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) lu_step_kernel(double* __restrict__ M, int ld, int k, int rem,
                                                                 double* __restrict__ rhs, double* __restrict__ dbuf,
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
                                                                 int* __restrict__ claims, int panel_sms, int inv_block) {
     constexpr int NT = WORKERS ? 256 : LU_THREADS;   // threads per CTA; the panel roles always run on threads 0..127
     static_assert(!(WORKERS && (FIRST || PASSES != 1)), "workers take one panel per visit");
-    static_assert(!(SPLIT && (WORKERS || PASSES != 1)), "split panel tiles belong to the chain-bound launches");
+    static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "CTAs per panel tile");
+    static_assert(!(SPLIT > 1 && (WORKERS || PASSES != 1)), "split panel tiles belong to the chain-bound launches");
     // programmatic dependent launch: the CTAs of block step k+1 are placed on the SMs while step k drains and start the moment
     // its memory is visible, instead of paying the launch latency between two launches of the chain (no-ops in a plain launch)
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -614,24 +615,23 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
     // the diagonal block like a panel CTA and runs beside them; with the inversion inside the diag CTA that CTA was the last
     // of a chain-bound launch to finish (by 5-16 k cycles for trailing matrices of 24-46 block rows).
     enum { DIAG, LCOL, UROW, OTHER, INV } role;
-    // SPLIT: two CTAs per panel tile (and two for the inverse).  Both update the whole tile (the tensor work is not on anybody's
-    // critical path here), then each solves 32 of its 64 independent rows (L tiles, inverse) or columns (U tiles): half the FMAs
-    // and shuffles per pivot of the issue-bound substitution.  Used while launches are chain-bound and SMs are idle anyway.
-    int half = 0;
-    const int npanel = SPLIT ? 4 * (rem - 1) : 2 * (rem - 1);
-    const int ninv = (inv_block >= 0) ? (SPLIT ? 2 : 1) : 0;
+    // SPLIT > 1: that many CTAs per panel tile (and for the inverse).  All update the whole tile (the tensor work is not on anybody's
+    // critical path here), then each solves 64 / SPLIT of its 64 independent rows (L tiles, inverse) or columns (U tiles): that
+    // fraction of the FMAs and shuffles per pivot of the issue-bound substitution.  Used while launches are chain-bound and SMs
+    // are idle anyway.
+    int half = 0;     // which part of the tile this CTA solves
+    const int npanel = 2 * SPLIT * (rem - 1);
+    const int ninv = (inv_block >= 0) ? SPLIT : 0;
     if (inv_block >= 0 && pb >= inv_block && pb < inv_block + ninv) {
         role = INV; bi = base; bj = base; half = pb - inv_block;
     } else if (pb == 0) {
         role = DIAG; bi = base; bj = base;
     } else if (pb <= npanel / 2) {
-        const int q = SPLIT ? (pb - 1) >> 1 : pb - 1;
-        half = SPLIT ? (pb - 1) & 1 : 0;
-        role = LCOL; bi = base + 1 + q; bj = base;
+        half = (pb - 1) % SPLIT;
+        role = LCOL; bi = base + 1 + (pb - 1) / SPLIT; bj = base;
     } else if (pb <= npanel) {
-        const int q = SPLIT ? (pb - 1 - npanel / 2) >> 1 : pb - 1 - npanel / 2;
-        half = SPLIT ? (pb - 1 - npanel / 2) & 1 : 0;
-        role = UROW; bi = base; bj = base + 1 + q;
+        half = (pb - 1 - npanel / 2) % SPLIT;
+        role = UROW; bi = base; bj = base + 1 + (pb - 1 - npanel / 2) / SPLIT;
     } else {
         role = OTHER;
         const int o = pb - (npanel + 1) - ninv;
@@ -754,7 +754,9 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         panel_sync<NT>();
     }
     const bool solves = !(role == DIAG && inv_block >= 0);
-    const bool whole = !SPLIT || role == DIAG;
+    const bool whole = SPLIT == 1 || role == DIAG;
+    constexpr int RI = 4 / SPLIT;            // register rows per thread of a part
+    constexpr int PR = 16 * RI;              // rows (columns) of a part
     const int ty = t >> 3, tx = t & 7;
     // 2-D cyclic register tile: a[i][j] <-> (row ty + 16 i, col tx + 8 j) of X; UROW works on the transposed tile
     const int sr = (role == UROW) ? 1 : TS, sc = (role == UROW) ? TS : 1;
@@ -781,21 +783,21 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
 #pragma unroll
             for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
     } else if (solves) {
-        // this CTA's half: rows (L tile, inverse) / columns (U tile) 32 half .. 32 half + 31, i.e. register rows 2 half, 2 half + 1
-        double a[2][8];
-        const int r0 = ty + 32 * half;
+        // this CTA's part: rows (L tile, inverse) / columns (U tile) PR half .. PR half + PR - 1, i.e. register rows RI half ..
+        double a[RI][8];
+        const int r0 = ty + PR * half;
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < RI; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 a[i][j] = (role == INV) ? ((r0 + 16 * i == tx + 8 * j) ? 1.0 : 0.0) : sC[(r0 + 16 * i) * sr + (tx + 8 * j) * sc];
         LU_CLK(6);
-        if (role == UROW) panel_solve<true, 2>(a, sA, dinv);
-        else panel_solve<false, 2>(a, sA, dinv);
+        if (role == UROW) panel_solve<true, RI>(a, sA, dinv);
+        else panel_solve<false, RI>(a, sA, dinv);
         LU_CLK(7);
         panel_sync<NT>();
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < RI; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) sC[(r0 + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
     }
@@ -805,16 +807,17 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         const size_t ldd = (role == DIAG || role == INV) ? (size_t)NB : (size_t)ld;
         if (whole) {
             store_tile(dst, ldd, sC);
-        } else if (role != UROW) {      // rows 32 half .. +31, all 64 columns: 32 x 32 double2
+        } else if (role != UROW) {      // rows PR half .. +PR-1, all 64 columns
             const int c2 = t & 31, rr = t >> 5;
 #pragma unroll 4
-            for (int r = 32 * half + rr; r < 32 * half + 32; r += 4)
+            for (int r = PR * half + rr; r < PR * half + PR; r += 4)
                 *reinterpret_cast<double2*>(dst + (size_t)r * ldd + 2 * c2) = *reinterpret_cast<const double2*>(sC + r * TS + 2 * c2);
-        } else {                        // all 64 rows, columns 32 half .. +31: 64 x 16 double2
-            const int c2 = t & 15, rr = t >> 4;
+        } else {                        // all 64 rows, columns PR half .. +PR-1 (PR / 2 double2 per row)
+            constexpr int W2 = PR / 2;
+            const int c2 = t % W2, rr = t / W2;
 #pragma unroll 4
-            for (int r = rr; r < NB; r += 8)
-                *reinterpret_cast<double2*>(dst + (size_t)r * ldd + 32 * half + 2 * c2) = *reinterpret_cast<const double2*>(sC + r * TS + 32 * half + 2 * c2);
+            for (int r = rr; r < NB; r += LU_THREADS / W2)
+                *reinterpret_cast<double2*>(dst + (size_t)r * ldd + PR * half + 2 * c2) = *reinterpret_cast<const double2*>(sC + r * TS + PR * half + 2 * c2);
         }
     }
     LU_CLK(8);
@@ -1189,6 +1192,7 @@ static bool g_chain_guard = true;     // LLS_LU_CHAIN_GUARD=0: update CTAs do no
 static int g_worker_reserve = 48;     // LLS_LU_WORKER_RESERVE: CTA slots left to the panel tiles at the start of a launch
 
 static int g_pack_min_rem = 0;        // LLS_LU_PACK_MIN_REM: trailing matrices of at least this many block rows claim roles by SM (0 = never, the default: the claim at CTA start costs more than the isolation returns, 2.83 -> 2.95 ms at N = 4000)
+static int g_split4_max_rem = 8;      // LLS_LU_SPLIT4_MAX_REM: ... and four CTAs per panel tile up to this (N = 200 0.107 -> 0.103 ms, N = 1000 0.432 -> 0.422 ms; slower again from 16 up)
 static int g_split_max_rem = 36;      // LLS_LU_SPLIT_MAX_REM: trailing matrices of at most this many block rows use two CTAs per panel tile (0 = never)
 static bool g_lu_inv_cta = true;      // LLS_LU_INV_CTA=0: the diag CTA inverts U11 itself after publishing
 static bool g_lu_pdl = true;          // LLS_LU_PDL=0: plain stream-ordered launches of the block steps
@@ -1218,6 +1222,8 @@ static int lu_prepare(Scene* s) {
         if (env != nullptr && atoi(env) >= 1) g_worker_chunk = atoi(env);
         env = getenv("LLS_LU_PACK_MIN_REM");
         if (env != nullptr) g_pack_min_rem = atoi(env);
+        env = getenv("LLS_LU_SPLIT4_MAX_REM");
+        if (env != nullptr) g_split4_max_rem = atoi(env);
         env = getenv("LLS_LU_SPLIT_MAX_REM");
         if (env != nullptr) g_split_max_rem = atoi(env);
         env = getenv("LLS_LU_INV_CTA");
@@ -1237,8 +1243,10 @@ static int lu_prepare(Scene* s) {
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_BYTES));
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         g_attr_done = true;
     }
     (void)s;
@@ -1277,9 +1285,14 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     const bool split_ok = (ncases == 1);           // a batch hides the chain of one case behind the other cases: no redundant tile updates there
     {
         const int rem = nblk;       // block 0 and its panel
-        if (split_ok && rem <= g_split_max_rem) {
+        if (split_ok && rem <= g_split4_max_rem) {
+            const int roles = 1 + 8 * (rem - 1);
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false, 4>, dim3(roles + 4 * inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+                    M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
+                    inv_cta ? roles : -1));
+        } else if (split_ok && rem <= g_split_max_rem) {
             const int roles = 1 + 4 * (rem - 1);
-            LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false, true>, dim3(roles + 2 * inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
+            LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false, 2>, dim3(roles + 2 * inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                     M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
                     inv_cta ? roles : -1));
         } else {
@@ -1324,11 +1337,17 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             k += 2;
         } else {
             const int psm = (g_pack_min_rem > 0 && rem >= g_pack_min_rem) ? (2 * rem - 2 + 2) / 3 : 0;
-            if (split_ok && !psm && rem <= g_split_max_rem) {     // chain-bound regime: two CTAs per panel tile and for the inverse
-                const int roles = 1 + 4 * (rem - 1);
-                LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false, true>, dim3(roles + 2 * inv_cta + (rem - 1) * (rem - 1), 1, ncases), LU_THREADS,
-                    (size_t)2 * TILE_BYTES, st, M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm,
-                    nullptr, 0, inv_cta ? roles : -1));
+            if (split_ok && !psm && rem <= g_split_max_rem) {     // chain-bound regime: 2 or 4 CTAs per panel tile and for the inverse
+                const int parts = (rem <= g_split4_max_rem) ? 4 : 2;
+                const int roles = 1 + 2 * parts * (rem - 1);
+                const dim3 grid(roles + parts * inv_cta + (rem - 1) * (rem - 1), 1, ncases);
+                if (parts == 4) {
+                    LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false, 4>, grid, LU_THREADS, (size_t)2 * TILE_BYTES, st, M, ld, k, rem, rhs, dbuf,
+                        s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0, inv_cta ? roles : -1));
+                } else {
+                    LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false, 2>, grid, LU_THREADS, (size_t)2 * TILE_BYTES, st, M, ld, k, rem, rhs, dbuf,
+                        s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0, inv_cta ? roles : -1));
+                }
                 count_launch();
                 k += 1;
                 continue;
