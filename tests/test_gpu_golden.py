@@ -195,3 +195,22 @@ def test_c2_full_size_properties():
             assert abs(a[comp] - b[comp]) <= 1e-9 * scale, (wing, comp)
         for comp in (1, 7):                        # side force: opposite
             assert abs(a[comp] + b[comp]) <= 1e-9 * scale, (wing, comp)
+
+
+@pytest.mark.parametrize("env", [
+    {"LLS_LU_WORKER_MIN_REM": "8", "LLS_LU_WORKER_CHUNK": "3"},      # persistent trailing-update workers
+    {"LLS_LU_PACK_MIN_REM": "8"},                                     # panel roles claimed by SM
+    {"LLS_LU_SPLIT_MAX_REM": "0", "LLS_LU_INV_CTA": "0", "LLS_LU_CHAIN_GUARD": "0", "LLS_LU_PDL": "0", "LLS_LU_PAIRS": "0"},   # plain
+    {"LLS_LU_SPLIT_MAX_REM": "64", "LLS_LU_SPLIT4_MAX_REM": "64"},  # four CTAs per panel tile everywhere
+])
+def test_lu_switchable_variants(env):
+    """The measured alternatives of the LU that stay in the tree behind environment switches must keep
+    factoring correctly: each runs scripts/lu_bench.py in a process of its own (the switches are read once per process)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for n in (300, 2500):
+        out = subprocess.run([sys.executable, os.path.join(root, "scripts", "lu_bench.py"), str(n), "1"], capture_output=True, text=True,
+                             timeout=300, cwd=root, env=dict(os.environ, **env))
+        assert out.returncode == 0, out.stderr[-2000:]
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        assert res["rel_residual"] < 1e-12, (env, res)
