@@ -178,3 +178,18 @@ def test_sweep_state_blocks_vectorised_equal_per_state():
     assert abs(scene._airplanes[name].get_aerodynamic_state()[0] - 2.0) < 1e-12
     with pytest.raises(ValueError):
         scene._batch_rows(name, [{"position": [1.0, 0.0, 0.0], "velocity": 100.0, "alpha": 1.0}])
+
+
+# ---- error behaviour of the drop-in API that needs no device (scene.py:1449-1450, 3864-3884) -----------------------------------
+def test_empty_scene_and_bad_requests_fail_like_the_reference():
+    empty = Scene({"scene": {"atmosphere": {}}})
+    with pytest.raises(RuntimeError, match="no aircraft"):
+        empty.solve_forces()                                   # scene.py:1449-1450
+    with pytest.raises(RuntimeError, match="no aircraft"):
+        empty.solve_forces_batch([{"velocity": 10.0}])
+    scene = _scene()
+    with pytest.raises(ValueError):                            # a batch keeps the geometry: the position may not move
+        scene._batch_rows("test_plane", [{"position": [0.0, 0.0, -10.0], "velocity": 100.0}])
+    with pytest.raises(NotImplementedError):                   # batched stencils report body and wind frames only
+        scene._batched_ok({"batched": True, "stab_frame": True})
+    assert scene._batched_ok({}) is False and scene._batched_ok({"batched": True}) is True
