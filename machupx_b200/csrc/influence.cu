@@ -124,6 +124,10 @@ __device__ __forceinline__ Vec3 joint_corner(const Vec3& Pe, const Vec3& tangent
     return Pe + (cdj * rsqrt(dot(uj, uj))) * uj;
 }
 
+#ifndef INF_UNROLL
+#define INF_UNROLL 1
+#endif
+constexpr int kInfUnroll = INF_UNROLL;   // rows per trip of the control-point loop; 2 spills more and is slower (0.543 -> 0.595 ms at C2)
 #ifndef INF_MIN_BLOCKS
 #define INF_MIN_BLOCKS 4   // 128 registers: 16 warps per SM; measured 0.61 ms vs 0.76 ms at 2 blocks (C2), slower again at 5-6 (spills)
 #endif
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
     const double guard = fmax(thr, 1e-13);
     const double inv4pi = 0.25 / 3.14159265358979323846;
 
+#pragma unroll kInfUnroll
     for (int r = 0; r < nrows; ++r) {
         const int i = row0 + r;
         const Vec3 pc{rs.pc[0][r], rs.pc[1][r], rs.pc[2][r]};
