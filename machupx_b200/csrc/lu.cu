@@ -1182,7 +1182,7 @@ extern "C" int lls_debug_lu_clocks(long long* out, int steps) {
 #endif
 
 static bool g_attr_done = false;
-constexpr int LU_PAIR_MIN_REM = 64;
+static int g_pair_min_rem = 64;       // LLS_LU_PAIR_MIN_REM: rank-128 paired visits for trailing matrices of at least this many block rows
 static bool g_lu_pairs = true;   // LLS_LU_PAIRS=0 falls back to one rank-64 update per launch
 static int g_worker_min_rem = 0;     // LLS_LU_WORKER_MIN_REM: trailing matrices of at least this many block rows use persistent workers (0 = never, the default: measured no faster than the tile-per-CTA kernel)
 static int g_worker_chunk = 2;       // LLS_LU_WORKER_CHUNK: consecutive serpentine tiles per grab
@@ -1222,6 +1222,8 @@ static int lu_prepare(Scene* s) {
         if (env != nullptr && atoi(env) >= 1) g_worker_chunk = atoi(env);
         env = getenv("LLS_LU_PACK_MIN_REM");
         if (env != nullptr) g_pack_min_rem = atoi(env);
+        env = getenv("LLS_LU_PAIR_MIN_REM");
+        if (env != nullptr && atoi(env) >= 2) g_pair_min_rem = atoi(env);
         env = getenv("LLS_LU_SPLIT4_MAX_REM");
         if (env != nullptr) g_split4_max_rem = atoi(env);
         env = getenv("LLS_LU_SPLIT_MAX_REM");
@@ -1320,7 +1322,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
         }
         // pairs pay off once the bulk of a launch outweighs the exposed chain of the thin launch (measured on B200: N = 16000
         // 123 -> 113 ms, N = 8000 17.1 -> 16.5 ms, N = 4000 3.25 -> 3.33 ms when pairing everything)
-        if (rem >= LU_PAIR_MIN_REM && g_lu_pairs) {
+        if (rem >= g_pair_min_rem && g_lu_pairs) {
             // thin launch: block row / column k+1 only (update with panel k, factor panel k+1) ...
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(2 * rem - 1 + inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                 M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0,
