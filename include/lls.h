@@ -40,6 +40,7 @@ extern "C" {
 #define LLS_STATUS_IMPINGEMENT 2
 #define LLS_STATUS_NAN 4
 #define LLS_STATUS_SMALL_PIVOT 8
+#define LLS_STATUS_BITS 5 /* number of status bits defined below */
 #define LLS_STATUS_SECTION_BOUNDS 16 /* a poly_fit airfoil was evaluated outside the limits of its fit (airfoil_db: PolyFitBoundsError) */
 
 /* ---- solver flags (reference: scene.py:82-87) ------------------------------------------ */
@@ -47,6 +48,7 @@ extern "C" {
 #define LLS_FLAG_TOTAL_VELOCITY 2
 #define LLS_FLAG_IN_PLANE 4
 #define LLS_FLAG_MATCH_MACHUP_PRO 8
+#define LLS_FLAG_CONSTRAIN_VORTEX_SHEET 16 /* trailing directions projected off the body z axis and renormalised (scene.py:595-611) */
 #define LLS_FLAG_DEFAULT (LLS_FLAG_SWEPT_SECTIONS | LLS_FLAG_TOTAL_VELOCITY | LLS_FLAG_IN_PLANE)
 
 /* ---- per-control-point double table fields --------------------------------------------- */
@@ -126,7 +128,8 @@ enum lls_aircraft_field {
     LLS_AC_W = 3,      /* 3: angular rate rotated to earth axes, R^-1(q) w (scene.py:569)     */
     LLS_AC_POS = 6,    /* 3: earth-fixed position p_bar (scene.py:442)                        */
     LLS_AC_CGR = 9,    /* 3: CG rotated to earth axes (scene.py:579)                          */
-    LLS_AC_STRIDE = 12
+    LLS_AC_ZF = 12,    /* 3: body z axis in earth axes (scene.py:601), read only with LLS_FLAG_CONSTRAIN_VORTEX_SHEET; [15] is padding */
+    LLS_AC_STRIDE = 16
 };
 
 /* ---- per-control-point solution table (outputs), field-major with the same ld ------------ */
@@ -258,8 +261,13 @@ int lls_integrate(lls_scene* h, double* d_seg_fm, void* stream);
 
 /* Status bits accumulated since the last lls_flow_state (device flag read back; synchronises). */
 int lls_get_status(lls_scene* h, void* stream, int* status);
+/* Byte offset of the device status word inside the caller's work buffer (so the host can fetch it together with the force sums,
+ * in the same synchronisation, instead of paying a second round trip through lls_get_status). */
+int lls_status_offset(lls_scene* h, size_t* offset_bytes);
 
-/* Dense FP64 LU (no pivoting across blocks; growth/NaN guard) on a row-major n x n matrix with
+/* Dense FP64 LU (no pivoting; guarded: a zero / NaN pivot raises LLS_STATUS_NAN, and a pivot more than six orders of
+ * magnitude below the largest pivot of the factorisation raises LLS_STATUS_SMALL_PIVOT in the scene's status word, where
+ * LAPACK's partial pivoting would have started to swap rows) on a row-major n x n matrix with
  * leading dimension ld, in place, then triangular solves for one right-hand side.
  * Stands in for numpy.linalg.solve -> LAPACK dgesv at scene.py:827 and scene.py:896. */
 int lls_lu_factor(lls_scene* h, double* d_mat, void* stream);

@@ -5,7 +5,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblls.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class LlsError(RuntimeError):
@@ -50,6 +50,7 @@ SIGNATURES = {
     "lls_solve_nonlinear": (_i, [_vp, _d, _d, _i, _vp, _pi, _pd, _pi, _pd]),
     "lls_integrate": (_i, [_vp, _vp, _vp]),
     "lls_get_status": (_i, [_vp, _vp, _pi]),
+    "lls_status_offset": (_i, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
     "lls_lu_factor": (_i, [_vp, _vp, _vp]),
     "lls_lu_solve": (_i, [_vp, _vp, _vp, _vp]),
     "lls_set_timing": (_i, [_vp, _i]),

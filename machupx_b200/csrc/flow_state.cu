@@ -15,7 +15,6 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
     out = case_ptr(out, cs.out);
     status = case_work_ptr(status, cs.work);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *status = 0;
     if (i >= ld) return;
     if (i >= n) {  // benign padding so full-ld kernels never see garbage
         for (int f = 0; f < W_NF; ++f) W[(size_t)f * ld + i] = 0.0;
@@ -45,8 +44,19 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
     st3(W, ld, W_UINF, i, (1.0 / vinf_mag) * vinf);
     {   // trailing directions (scene.py:591-592); a true division like the reference
         double m0 = norm(j0), m1 = norm(j1);
-        st3(out, ld, LLS_O_UTRAIL0, i, Vec3{j0.x / m0, j0.y / m0, j0.z / m0});
-        st3(out, ld, LLS_O_UTRAIL1, i, Vec3{j1.x / m1, j1.y / m1, j1.z / m1});
+        Vec3 u0{j0.x / m0, j0.y / m0, j0.z / m0}, u1{j1.x / m1, j1.y / m1, j1.z / m1};
+        if (flags & LLS_FLAG_CONSTRAIN_VORTEX_SHEET) {                           // scene.py:595-611
+            // the sheet is kept in the aircraft's x-y plane: project the body z axis (earth axes) out, then renormalise
+            const Vec3 zf{a[LLS_AC_ZF], a[LLS_AC_ZF + 1], a[LLS_AC_ZF + 2]};
+            u0 = u0 - dot(zf, u0) * zf;
+            u1 = u1 - dot(zf, u1) * zf;
+            m0 = norm(u0);
+            m1 = norm(u1);
+            u0 = Vec3{u0.x / m0, u0.y / m0, u0.z / m0};
+            u1 = Vec3{u1.x / m1, u1.y / m1, u1.z / m1};
+        }
+        st3(out, ld, LLS_O_UTRAIL0, i, u0);
+        st3(out, ld, LLS_O_UTRAIL1, i, u1);
     }
     const Vec3 us = ld3(tab, ld, LLS_F_US, i), ua = ld3(tab, ld, LLS_F_UA, i), un = ld3(tab, ld, LLS_F_UN, i);
     double vinf_ip = vinf_mag, vir_ip = vir_mag;
@@ -78,6 +88,10 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
 
 int launch_flow_state(Scene* s, cudaStream_t st) {
     int block = 128, grid = (s->ld + block - 1) / block;
+    // the status word of every case is cleared in stream order BEFORE the launch: blocks of this launch set bits in it (section
+    // bounds), and a reset from inside the kernel could wipe a bit another block had already set
+    if (s->ncases > 1) LLS_CUDA_TRY(cudaMemset2DAsync(s->status, s->cs.work, 0, sizeof(int), (size_t)s->ncases, st));
+    else LLS_CUDA_TRY(cudaMemsetAsync(s->status, 0, sizeof(int), st));
     flow_state_kernel<<<dim3(grid, 1, s->ncases), block, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->ac, s->W, s->out, s->status,
                                                                   strides(s, false));
     count_launch();

@@ -54,7 +54,7 @@ static int read_scalars(Scene* s, cudaStream_t st, int count) {
 using namespace lls;
 
 extern "C" const char* lls_last_error(void) { return lls::g_err; }
-extern "C" int lls_abi_version(void) { return 2; }
+extern "C" int lls_abi_version(void) { return 3; }
 extern "C" unsigned long long lls_launch_count(void) { return lls::g_launches; }
 
 extern "C" int lls_query_sizes(int n, int n_segments, lls_sizes* out) {
@@ -419,6 +419,12 @@ extern "C" int lls_get_status(lls_scene* h, void* stream, int* status) {
     cudaStream_t st = (cudaStream_t)stream;
     LLS_CUDA_TRY(cudaMemcpyAsync(status, h->status, sizeof(int), cudaMemcpyDeviceToHost, st));
     LLS_CUDA_TRY(cudaStreamSynchronize(st));
+    return LLS_OK;
+}
+
+extern "C" int lls_status_offset(lls_scene* h, size_t* offset_bytes) {
+    LLS_REQUIRE(h != nullptr && h->W != nullptr && offset_bytes != nullptr, LLS_ERR_STATE, "lls_status_offset: scene not bound");
+    *offset_bytes = (size_t)((const char*)h->status - (const char*)h->W);     // W is the start of the caller's work buffer
     return LLS_OK;
 }
 

@@ -352,6 +352,46 @@ __device__ __forceinline__ void forward_rhs_warp(const double* __restrict__ sC, 
     b[lane + 32] = x1;
 }
 
+// Growth guard of the unpivoted factorisation, run by the diag CTA off the critical path (after the block is published):
+// scalars[1] / scalars[2] carry the smallest / largest pivot magnitude of the factorisation so far; a zero or NaN pivot raises
+// LLS_STATUS_NAN (LAPACK: "singular matrix"), and after the last diagonal block a smallest pivot below PIVOT_RATIO times the
+// largest raises LLS_STATUS_SMALL_PIVOT: the matrix is not the diagonally dominant one the solver relies on (the lifting-line
+// systems have pivot ratios of O(10)) and partial pivoting would have started to matter.
+constexpr double PIVOT_RATIO = 1e-6;
+template <int NT>
+__device__ __forceinline__ void pivot_guard(const double* __restrict__ sC, PivotLine& pl, int blk, int nblk, double* __restrict__ scalars,
+                                            int* __restrict__ status) {
+    const int t = threadIdx.x;
+    if (t < NB) {
+        const double d = fabs(sC[t * TS + t]);
+        // the identity padding beyond n contributes pivots of exactly 1: they say nothing about the matrix and are left out
+        double m = (d == 1.0) ? 1.0e300 : d, M = (d == 1.0) ? 0.0 : d;
+        bool bad = !(d > 0.0) || !(d < 1.0e300);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if ((t & 31) == 0) {
+            if (bad) atomicOr(status, LLS_STATUS_NAN);
+            pl.piv[t >> 5] = m;
+            pl.rcp[t >> 5] = M;        // (the reciprocal pivots were consumed before the block was published)
+        }
+    }
+    panel_sync<NT>();
+    if (t == 0) {
+        double m = fmin(pl.piv[0], pl.piv[1]), M = fmax(pl.rcp[0], pl.rcp[1]);
+        if (blk > 0) {
+            m = fmin(m, scalars[1]);
+            M = fmax(M, scalars[2]);
+        }
+        scalars[1] = m;
+        scalars[2] = M;
+        if (blk == nblk - 1 && m < PIVOT_RATIO * M) atomicOr(status, LLS_STATUS_SMALL_PIVOT);
+    }
+}
+
 // ---- keeping the serial chain's SM to itself ---------------------------------------------------------------------------
 // The in-register factorisation of the diagonal block is latency- and FP64-issue-bound on ONE CTA; trailing-update CTAs that
 // share its SM keep the FP64 pipe busy with DMMA and stretch it 2-3.5x (measured per block step with scripts/lu_clocks.py:
@@ -717,23 +757,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         LU_CLK(5);
         // everything below is off the critical path of the panel CTAs
         store_tile(gC, ld, sC);
-        if (t < NB) {       // smallest pivot magnitude and zero / NaN pivots (growth guard of the unpivoted factorisation)
-            const double d = fabs(sC[t * TS + t]);
-            double m = d;
-            bool bad = !(d > 0.0);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
-            bad = __any_sync(0xffffffffu, bad);
-            if ((t & 31) == 0) {
-                if (bad) atomicOr(status, LLS_STATUS_NAN);
-                pl.piv[t >> 5] = m;
-            }
-        }
-        panel_sync<NT>();
-        if (t == 0) {
-            const double m = fmin(pl.piv[0], pl.piv[1]);
-            scalars[1] = (blk == 0) ? m : fmin(m, scalars[1]);
-        }
+        pivot_guard<NT>(sC, pl, blk, ld / NB, scalars, status);
         if (rhs != nullptr && t < 32) forward_rhs_warp(sC, rhs + (size_t)blk * NB);
         // W = U11, pre-scaled rows in sA: the solve below turns the identity into inv(U11) (unless an INV CTA does that)
     } else {
@@ -987,23 +1011,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_owner_kernel(double* __
         __syncthreads();
         if (t == 0) st_release(flags + k, epoch);
         store_tile(gC, ld, sC);
-        if (t < NB) {
-            const double d = fabs(sC[t * TS + t]);
-            double m = d;
-            bool bad = !(d > 0.0);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
-            bad = __any_sync(0xffffffffu, bad);
-            if ((t & 31) == 0) {
-                if (bad) atomicOr(status, LLS_STATUS_NAN);
-                pl.piv[t >> 5] = m;
-            }
-        }
-        __syncthreads();
-        if (t == 0) {
-            const double m = fmin(pl.piv[0], pl.piv[1]);
-            scalars[1] = (k == 0) ? m : fmin(m, scalars[1]);
-        }
+        pivot_guard<LU_THREADS>(sC, pl, k, ld / NB, scalars, status);
         if (rhs != nullptr && t < 32) {
             forward_rhs_warp(sC, rhs + (size_t)k * NB);
             __syncwarp();

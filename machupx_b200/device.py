@@ -51,12 +51,17 @@ class DeviceScene:
             self.d_seg_fm = torch.zeros((self.n_segments, 12), dtype=torch.float64, device=dev)
             self.h_ac = torch.zeros((self.n_aircraft, L.AC_STRIDE), dtype=torch.float64).pin_memory()
             self.h_seg_fm = torch.zeros((self.n_segments, 12), dtype=torch.float64).pin_memory()
+            self.h_status = torch.zeros(1, dtype=torch.int32).pin_memory()
             _native.check(self.lib.lls_bind(self.handle, _ptr(self.d_tab), _ptr(self.d_itab), _ptr(self.d_af), _ptr(self.d_out),
                                             _ptr(self.d_V), _ptr(self.d_M), _ptr(self.d_work), ctypes.c_size_t(sizes.work_bytes)))
             _native.check(self.lib.lls_set_state(self.handle, _ptr(self.d_ac)))
+            off = ctypes.c_size_t(0)
+            _native.check(self.lib.lls_status_offset(self.handle, ctypes.byref(off)))
+            self.d_status = self.d_work[off.value:off.value + 4].view(torch.int32)
         self.upload_tables(tables)
         self.bytes_h2d = 0
         self.bytes_d2h = 0
+        self.last_status = 0
 
     def __del__(self):
         try:
@@ -83,7 +88,7 @@ class DeviceScene:
             self.d_tab[f].copy_(torch.from_numpy(np.ascontiguousarray(tab[f], dtype=np.float64)))
 
     def upload_state(self, ac_state):
-        self.h_ac.copy_(torch.from_numpy(np.ascontiguousarray(ac_state, dtype=np.float64).reshape(self.n_aircraft, L.AC_STRIDE)))
+        self.h_ac.copy_(torch.from_numpy(np.ascontiguousarray(L.pad_ac_state(ac_state)).reshape(self.n_aircraft, L.AC_STRIDE)))
         self.d_ac.copy_(self.h_ac, non_blocking=True)
         self.bytes_h2d += self.h_ac.numel() * 8
 
@@ -122,8 +127,10 @@ class DeviceScene:
         with torch.cuda.device(self.device):
             _native.check(self.lib.lls_integrate(self.handle, _ptr(self.d_seg_fm), self._stream()))
             self.h_seg_fm.copy_(self.d_seg_fm, non_blocking=True)
+            self.h_status.copy_(self.d_status, non_blocking=True)      # status word after the integration, same synchronisation
             torch.cuda.current_stream(self.device).synchronize()
-        self.bytes_d2h += self.h_seg_fm.numel() * 8
+        self.bytes_d2h += self.h_seg_fm.numel() * 8 + 4
+        self.last_status = int(self.h_status[0])
         return self.h_seg_fm.numpy().copy()
 
     def status(self):
@@ -218,8 +225,20 @@ class BatchDeviceScene:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def upload_tables(self, tables):
+        """Shared geometry / control / atmosphere tables of every case of the batch."""
+        af = np.ascontiguousarray(tables["airfoils"], dtype=np.float64).reshape(-1, L.AF_STRIDE)
+        assert af.shape[0] == self.n_airfoils
+        self.d_tab.copy_(torch.from_numpy(np.ascontiguousarray(tables["tab"], dtype=np.float64)))
+        self.d_itab.copy_(torch.from_numpy(np.ascontiguousarray(tables["itab"], dtype=np.int32)))
+        self.d_af.copy_(torch.from_numpy(af))
+
+    def upload_rows(self, tab, fields):
+        for f in fields:
+            self.d_tab[f].copy_(torch.from_numpy(np.ascontiguousarray(tab[f], dtype=np.float64)))
+
     def upload_states(self, ac_states):
-        self.h_ac.copy_(torch.from_numpy(np.ascontiguousarray(ac_states, dtype=np.float64).reshape(self.ncases, self.n_aircraft, L.AC_STRIDE)))
+        self.h_ac.copy_(torch.from_numpy(np.ascontiguousarray(L.pad_ac_state(np.asarray(ac_states, dtype=np.float64).reshape(self.ncases, self.n_aircraft, -1)))))
         self.d_ac.copy_(self.h_ac, non_blocking=True)
 
     def solve(self, solver_type, convergence, relaxation, max_iterations, impingement_threshold=1e-10, linear_start=True):
@@ -242,9 +261,10 @@ class BatchDeviceScene:
                 _native.check(self.lib.lls_get_status_batch(self.handle, st, status))
             _native.check(self.lib.lls_integrate(self.handle, _ptr(self.d_seg_fm), st))
             self.h_seg_fm.copy_(self.d_seg_fm, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
+            late = (ctypes.c_int * nc)()       # bits raised by the integration (section bounds of CD / Cm); synchronises the stream
+            _native.check(self.lib.lls_get_status_batch(self.handle, st, late))
         return (self.h_seg_fm.numpy().copy(), np.frombuffer(its, dtype=np.int32).copy(), np.frombuffer(err, dtype=np.float64).copy(),
-                np.frombuffer(status, dtype=np.int32).copy())
+                np.frombuffer(status, dtype=np.int32) | np.frombuffer(late, dtype=np.int32))
 
     def gamma(self):
         return self.d_out[:, L.O_GAMMA, :self.n].cpu().numpy()

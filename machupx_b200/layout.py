@@ -11,6 +11,7 @@ F_SPC, F_SP0, F_SP1, F_SIGMA, F_CDJ0, F_CDJ1, F_CBAR, F_DS, F_CSWI = 39, 40, 41,
 F_RHO, F_NU, F_SOS, F_VWIND = 48, 49, 50, 51
 F_WB, F_FLAP_DA, F_FLAP_DCM, F_FLAP_DCD, F_FLAP_DEFL, F_FLAP_CF = 54, 55, 56, 57, 58, 59
 NF = 60
+FLAP_FIELDS = (F_FLAP_DA, F_FLAP_DCM, F_FLAP_DCD, F_FLAP_DEFL, F_FLAP_CF)   # the rows that change with the control state only
 
 # per-control-point int32 fields (enum lls_ifield)
 I_WING_BEGIN, I_WING_END, I_AIRCRAFT, I_REID, I_SEGMENT, I_AFA, I_AFB = 0, 1, 2, 3, 4, 5, 6
@@ -23,8 +24,8 @@ AF_STRIDE = 16
 POLY_DOF_KINDS = ("alpha", "Rey", "Mach", "trailing_flap_deflection", "trailing_flap_fraction")
 
 # per-aircraft state block (enum lls_aircraft_field)
-AC_VTRANS, AC_W, AC_POS, AC_CGR = 0, 3, 6, 9
-AC_STRIDE = 12
+AC_VTRANS, AC_W, AC_POS, AC_CGR, AC_ZF = 0, 3, 6, 9, 12
+AC_STRIDE = 16
 
 # per-control-point output fields (enum lls_out_field)
 O_GAMMA, O_VI, O_ALPHA, O_CL, O_CD, O_CM, O_RE, O_MACH = 0, 1, 4, 5, 6, 7, 8, 9
@@ -33,13 +34,30 @@ O_AL0, O_REDIM_IP, O_REDIM_FULL, O_UTRAIL0, O_UTRAIL1, O_R, O_VI2 = 22, 23, 24, 
 NO = 33
 
 # solver flags
-FLAG_SWEPT_SECTIONS, FLAG_TOTAL_VELOCITY, FLAG_IN_PLANE, FLAG_MATCH_MACHUP_PRO = 1, 2, 4, 8
+FLAG_SWEPT_SECTIONS, FLAG_TOTAL_VELOCITY, FLAG_IN_PLANE, FLAG_MATCH_MACHUP_PRO, FLAG_CONSTRAIN_VORTEX_SHEET = 1, 2, 4, 8, 16
 FLAG_DEFAULT = FLAG_SWEPT_SECTIONS | FLAG_TOTAL_VELOCITY | FLAG_IN_PLANE
 
 # status bits
 STATUS_NOT_CONVERGED, STATUS_IMPINGEMENT, STATUS_NAN, STATUS_SMALL_PIVOT, STATUS_SECTION_BOUNDS = 1, 2, 4, 8, 16
+STATUS_BITS = 5
 
 LD_ALIGN = 64  # leading dimension is N rounded up to this many elements
+
+
+def pad_ac_state(ac_state):
+    """(n_aircraft, AC_STRIDE) view of a state block; blocks written before the body-z-axis columns existed (12 doubles per
+    aircraft, as in the committed golden fixtures) are widened with zeros (the columns are read only with
+    FLAG_CONSTRAIN_VORTEX_SHEET)."""
+    import numpy as np
+    a = np.asarray(ac_state, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 12 if a.size % AC_STRIDE else AC_STRIDE)
+    if a.shape[-1] == AC_STRIDE:
+        return a
+    assert a.shape[-1] == 12, a.shape
+    out = np.zeros(a.shape[:-1] + (AC_STRIDE,))
+    out[..., :12] = a
+    return out
 
 
 def padded_ld(n):

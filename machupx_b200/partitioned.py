@@ -243,8 +243,20 @@ class PartitionedDeviceScene:
         with self.torch.cuda.device(self.device):
             self._native.check(fn(self.handle, *args))
 
+    def upload_tables(self, tables):
+        tables = repad_tables(tables, self.ld)
+        af = np.ascontiguousarray(tables["airfoils"], dtype=np.float64).reshape(-1, L.AF_STRIDE)
+        self.d_tab.copy_(self.torch.from_numpy(np.ascontiguousarray(tables["tab"], dtype=np.float64)))
+        self.d_itab.copy_(self.torch.from_numpy(np.ascontiguousarray(tables["itab"], dtype=np.int32)))
+        self.d_af.copy_(self.torch.from_numpy(af))
+
+    def upload_rows(self, tab, fields):
+        n = self.n
+        for f in fields:
+            self.d_tab[f, :n].copy_(self.torch.from_numpy(np.ascontiguousarray(tab[f][:n], dtype=np.float64)))
+
     def upload_state(self, ac_state):
-        self.d_ac.copy_(self.torch.from_numpy(np.ascontiguousarray(ac_state, dtype=np.float64).reshape(self.n_aircraft, L.AC_STRIDE)))
+        self.d_ac.copy_(self.torch.from_numpy(np.ascontiguousarray(L.pad_ac_state(ac_state)).reshape(self.n_aircraft, L.AC_STRIDE)))
 
     # -- ops interface --------------------------------------------------------------------------------------------
     def flow_and_influence(self):
@@ -292,8 +304,8 @@ class PartitionedDeviceScene:
         seg = self.comm.all_reduce_sum(self.d_seg_fm.cpu().numpy())
         st = ctypes.c_int(0)
         self._call(self.lib.lls_get_status, self._st(), ctypes.byref(st))
-        flags = self.comm.all_reduce_sum(np.array([float((st.value >> b) & 1) for b in range(4)]))
-        status = sum((1 << b) for b in range(4) if flags[b] > 0)
+        flags = self.comm.all_reduce_sum(np.array([float((st.value >> b) & 1) for b in range(L.STATUS_BITS)]))
+        status = sum((1 << b) for b in range(L.STATUS_BITS) if flags[b] > 0)
         if failed:
             status |= L.STATUS_NOT_CONVERGED
         torch.cuda.synchronize(self.device)

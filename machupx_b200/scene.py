@@ -41,6 +41,14 @@ _IMPINGEMENT_TEXT = ("MachUpX detected a trailing vortex impinging upon a contro
                      "induced velocities at the control point. See \"Common Issues\" in the documentation for more information. "
                      "This warning can be suppressed by reducing \"impingement_threshold\" in the solver parameters.")
 
+_SMALL_PIVOT_TEXT = ("The unpivoted LU factorisation of the lifting-line system met a pivot more than six orders of magnitude below the "
+                     "largest one: the matrix is far from the diagonally dominant form the solver relies on (numpy.linalg.solve in "
+                     "the reference pivots), so the circulation and the forces may be inaccurate.")
+_NAN_TEXT = ("The lifting-line solve produced NaN (a zero or NaN pivot in the LU factorisation, or a NaN residual); the reference "
+             "propagates NaN silently in this situation (docs/source/common_issues.md).")
+
+_BOUNDS_TEXT = "A poly_fit airfoil was evaluated outside the limits of its fit."
+
 _FRAME_KEYS = {"body": ("Cx", "Cy", "Cz", "Cl", "Cm", "Cn"),
                "stab": ("Cx_s", "Cy_s", "Cz_s", "Cl_s", "Cm_s", "Cn_s"),
                "wind": ("CL", "CD", "CS", "Cl_w", "Cm_w", "Cn_w")}
@@ -62,6 +70,7 @@ class Scene:
         self._num_aircraft = 0
         self._solved = False
         self._device = None
+        self._device_revs = None
         self._tables = None
         self._out_cache = None
         self._FM = {}
@@ -98,8 +107,6 @@ class Scene:
         if self._solver_type == "scipy_fsolve":
             raise NotImplementedError("solver type 'scipy_fsolve' (scene.py:671-702) runs the residual on the host; this "
                                       "package has no CPU solve path. Use 'nonlinear' or 'linear'.")
-        if self._constrain_vortex_sheet:
-            raise NotImplementedError("'constrain_vortex_sheet' (scene.py:595-611) is not implemented on the device.")
 
         self._unit_sys = self._input_dict.get("units", "English")
         scene_dict = self._input_dict.get("scene", {})
@@ -206,6 +213,9 @@ class Scene:
         self._N -= gone.get_num_cps()
         self._num_aircraft -= 1
         self._device = None
+        self._device_revs = None
+        self._batch_device = None
+        self._part_device = None
         self._tables = None
         if self._num_aircraft != 0:
             self._store_aircraft_properties()
@@ -249,7 +259,8 @@ class Scene:
         self._tables = build_tables(self)
         self._pose_key = self._current_pose_key()
         self._controls_key = self._current_controls_key()
-        self._tables_uploaded = False
+        self._tables_rev = getattr(self, "_tables_rev", 0) + 1
+        self._tables_full_rev = getattr(self, "_tables_full_rev", 0) + 1
         self._solved = False
 
     def _current_pose_key(self):
@@ -264,10 +275,11 @@ class Scene:
     # ------------------------------------------------------------------------------------------------------
     # device plumbing
     # ------------------------------------------------------------------------------------------------------
-    def _sync_device(self):
-        """Brings the device tables in line with the host objects.  Drivers (derivatives, trim) change the airplane
-        objects directly, as in the reference, so state is compared here rather than trusted to setters."""
-        from .device import DeviceScene
+    def _refresh_tables(self):
+        """Brings the HOST tables in line with the airplane objects and returns the table revision.  Drivers (derivatives,
+        trim) change the airplane objects directly, as in the reference, so pose and control state are compared here rather
+        than trusted to setters.  Every consumer of the tables (single-scene, batch and partitioned device objects) keys its
+        uploads on the revision, so a control change can never leave a stale flap row on a device."""
         if self._current_pose_key() != self._pose_key:
             self._perform_geometry_and_atmos_calcs()
         elif self._current_controls_key() != self._controls_key:
@@ -275,17 +287,31 @@ class Scene:
             for f, values in rows.items():
                 self._tables["tab"][f, :self._N] = values
             self._controls_key = self._current_controls_key()
-            if self._device is not None and self._tables_uploaded:
-                self._device.upload_rows(self._tables["tab"], sorted(rows.keys()))
+            self._tables_rev += 1
+        return self._tables_rev
+
+    def _sync_device(self):
+        """Brings the single-scene device tables in line with the host objects and uploads the flight state."""
+        from .device import DeviceScene
+        self._refresh_tables()
+        rev = (self._tables_rev, self._tables_full_rev)
         if self._device is None or self._device.n != self._N or self._device.n_segments != self._tables["n_segments"] \
                 or self._device.n_airfoils != len(self._tables["airfoils"]) or self._device.n_aircraft != self._num_aircraft \
                 or self._device.flags != self._tables["flags"]:
             self._device = DeviceScene(self._tables)
-            self._tables_uploaded = True
-        elif not self._tables_uploaded:
-            self._device.upload_tables(self._tables)
-            self._tables_uploaded = True
+            self._device_revs = rev
+        self._device_revs = self._upload_if_stale(self._device, self._device_revs)
         self._device.upload_state(build_aircraft_state(self))
+
+    def _upload_if_stale(self, dev, have):
+        """Uploads to ``dev`` (anything with upload_tables / upload_rows) whatever changed in the host tables since revision
+        pair ``have`` = (revision, full revision); returns the pair now on the device."""
+        want = (self._tables_rev, self._tables_full_rev)
+        if have is None or have[1] != want[1]:
+            dev.upload_tables(self._tables)
+        elif have[0] != want[0]:
+            dev.upload_rows(self._tables["tab"], L.FLAP_FIELDS)      # only control deflections changed: five table rows
+        return want
 
     def __getattr__(self, name):
         spec = _LAZY_OUT.get(name)
@@ -319,6 +345,7 @@ class Scene:
         self._sync_device()
         dev = self._device
         linear_time = nonlinear_time = 0.0
+        status = 0
         try:
             # scene.py:557-668 (called from _solve_linear, or directly when the previous gamma seeds Newton)
             dev.flow_state()
@@ -339,15 +366,11 @@ class Scene:
                     print("".join(["-"] * 40))
                     for k, e in enumerate(hist):
                         print("{0:<20}{1:<20}".format(k + 1, e))
-                if status & L.STATUS_IMPINGEMENT:
-                    warnings.warn(_IMPINGEMENT_TEXT)
-                if status & L.STATUS_NOT_CONVERGED:
-                    raise SolverNotConvergedError(self._solver_type, err)
+                self._report_status(status, err)
                 if verbose: print("Nonlinear solver successfully converged. Final error: {0}".format(err))
-            elif dev.status() & L.STATUS_IMPINGEMENT:
-                warnings.warn(_IMPINGEMENT_TEXT)
-            if dev.status() & L.STATUS_SECTION_BOUNDS:
-                raise DatabaseBoundsError("A poly_fit airfoil was evaluated outside the limits of its fit.")
+            else:
+                status = dev.status()
+                self._report_status(status, 0.0)
         except Exception as e:
             self._handle_error(e)
 
@@ -355,6 +378,9 @@ class Scene:
         try:
             seg_fm = dev.integrate()
             self._seg_fm = seg_fm
+            if dev.last_status & L.STATUS_SECTION_BOUNDS and not status & L.STATUS_SECTION_BOUNDS:
+                # CD / Cm of the integration are evaluated at (alpha, Re, Mach) combinations the Newton loop never visited
+                self._handle_error(DatabaseBoundsError(_BOUNDS_TEXT))
             body, stab, wind = self._get_frames(**kwargs)
             self._FM = assemble_fm(seg_fm, self._frames(), non_dimensional=kwargs.get("non_dimensional", True),
                                    dimensional=kwargs.get("dimensional", True), report_by_segment=kwargs.get("report_by_segment", False),
@@ -388,17 +414,12 @@ class Scene:
         every rank gets the same ``FM``.  ``_gamma`` is replicated; the other per-point arrays are only filled for the rows a
         rank owns."""
         from .partitioned import PartitionedDeviceScene
-        if self._current_pose_key() != self._pose_key:
-            self._perform_geometry_and_atmos_calcs()
-        elif self._current_controls_key() != self._controls_key:
-            for f, values in flap_rows(self).items():
-                self._tables["tab"][f, :self._N] = values
-            self._controls_key = self._current_controls_key()
-            self._part_tables_id = None
+        self._refresh_tables()
         dev = getattr(self, "_part_device", None)
-        if dev is None or getattr(self, "_part_tables_id", None) != id(self._tables):
+        if dev is None or dev.n != self._N or dev.flags != self._tables["flags"] or dev.n_segments != self._tables["n_segments"]:
             dev = self._part_device = PartitionedDeviceScene(self._tables)
-            self._part_tables_id = id(self._tables)
+            self._part_revs = (self._tables_rev, self._tables_full_rev)
+        self._part_revs = self._upload_if_stale(dev, self._part_revs)
         dev.upload_state(build_aircraft_state(self))
         self._FM = {}
         self._out_cache = None
@@ -408,10 +429,7 @@ class Scene:
         self._device = None
         self._out_cache = dev.d_out[:, :self._N].cpu().numpy()
         try:
-            if status & L.STATUS_IMPINGEMENT:
-                warnings.warn(_IMPINGEMENT_TEXT)
-            if status & L.STATUS_NOT_CONVERGED:
-                raise SolverNotConvergedError(self._solver_type, err)
+            self._report_status(status, err)
         except Exception as e:
             self._handle_error(e)
         body, stab, wind = self._get_frames(**kwargs)
@@ -438,8 +456,7 @@ class Scene:
         if self._num_aircraft == 0:
             raise RuntimeError("There are no aircraft in this scene. No calculations can be performed.")
         name = self._only_aircraft(aircraft)
-        if self._current_pose_key() != self._pose_key:
-            self._perform_geometry_and_atmos_calcs()
+        self._refresh_tables()
         return self._solve_batch_rows(self._batch_rows(name, states), max_batch)
 
     def _batch_rows(self, name, states):
@@ -510,26 +527,39 @@ class Scene:
             hi = min(lo + max_batch, n_total)
             nc = hi - lo
             dev = getattr(self, "_batch_device", None)
-            if dev is None or dev.ncases != nc or dev.n != self._N or dev.flags != self._tables["flags"]:
+            if dev is None or dev.ncases != nc or dev.n != self._N or dev.flags != self._tables["flags"] \
+                    or dev.n_segments != self._tables["n_segments"] or dev.n_aircraft != self._num_aircraft:
                 dev = self._batch_device = BatchDeviceScene(self._tables, nc)
-                self._batch_tables_id = id(self._tables)
-            elif self._batch_tables_id != id(self._tables):
-                dev.d_tab.copy_(__import__("torch").from_numpy(np.ascontiguousarray(self._tables["tab"])))
-                self._batch_tables_id = id(self._tables)
+                self._batch_revs = (self._tables_rev, self._tables_full_rev)
+            self._batch_revs = self._upload_if_stale(dev, self._batch_revs)
             dev.upload_states(ac_states[lo:hi])
             seg_fm[lo:hi], its[lo:hi], err[lo:hi], status[lo:hi] = dev.solve(
                 self._solver_type, self._solver_convergence, self._solver_relaxation, self._max_solver_iterations,
                 self._impingement_threshold)
-        if (status & L.STATUS_IMPINGEMENT).any():
-            warnings.warn(_IMPINGEMENT_TEXT)
         converged = (status & L.STATUS_NOT_CONVERGED) == 0
-        if not converged.all():
-            try:
-                raise SolverNotConvergedError(self._solver_type, float(err[~converged].max()))
-            except SolverNotConvergedError as e:
-                self._handle_error(e)
+        try:
+            # one report for the whole batch: the union of the cases' status bits, the largest final error of the failed cases
+            self._report_status(int(np.bitwise_or.reduce(status)) if n_total else 0,
+                                float(err[~converged].max()) if not converged.all() else 0.0)
+        except Exception as e:
+            self._handle_error(e)
         return {"totals": batch_totals(seg_fm, ac_states, info), "iterations": its, "final_error": err, "converged": converged,
                 "status": status, "seg_fm": seg_fm}
+
+    def _report_status(self, status, err):
+        """Device status bits -> the reference's warnings and exceptions (scene.py:622-623, 905-908; wing_segment.py:1087), routed
+        through the error policy by the caller.  Bounds errors come first: the reference raises them from inside the residual."""
+        status = int(status)
+        if status & L.STATUS_IMPINGEMENT:
+            warnings.warn(_IMPINGEMENT_TEXT)
+        if status & L.STATUS_SMALL_PIVOT:
+            warnings.warn(_SMALL_PIVOT_TEXT)
+        if status & L.STATUS_NAN:
+            warnings.warn(_NAN_TEXT)
+        if status & L.STATUS_SECTION_BOUNDS:
+            self._handle_error(DatabaseBoundsError(_BOUNDS_TEXT))
+        if status & L.STATUS_NOT_CONVERGED:
+            raise SolverNotConvergedError(self._solver_type, err)
 
     def _frames(self):
         return [AircraftFrame(ap.name, ap.q, ap.v, self._get_wind(ap.p_bar), self._get_density(ap.p_bar), ap.S_w,
@@ -637,8 +667,7 @@ class Scene:
         geometry tables are shared by the cases); returns one {key: float} dictionary of aircraft totals per case, with the
         body- and wind-frame keys of ``_FM[name]["total"]``."""
         ap = self._airplanes[name]
-        if self._current_pose_key() != self._pose_key:
-            self._perform_geometry_and_atmos_calcs()
+        self._refresh_tables()
         saved = ap.get_state()
         rows = []
         try:

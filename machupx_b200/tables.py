@@ -72,6 +72,8 @@ def solver_flags(scene):
         f |= L.FLAG_IN_PLANE
     if scene._match_machup_pro:
         f |= L.FLAG_MATCH_MACHUP_PRO
+    if getattr(scene, "_constrain_vortex_sheet", False):
+        f |= L.FLAG_CONSTRAIN_VORTEX_SHEET
     return f
 
 
@@ -233,4 +235,5 @@ def build_aircraft_state(scene):
         st[ia, L.AC_W:L.AC_W + 3] = body_to_earth(q, np.asarray(ap.w, dtype=float))
         st[ia, L.AC_POS:L.AC_POS + 3] = np.asarray(ap.p_bar, dtype=float)
         st[ia, L.AC_CGR:L.AC_CGR + 3] = body_to_earth(q, np.asarray(ap.CG, dtype=float))
+        st[ia, L.AC_ZF:L.AC_ZF + 3] = body_to_earth(q, np.array([0.0, 0.0, 1.0]))      # scene.py:601
     return st

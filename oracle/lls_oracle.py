@@ -42,7 +42,7 @@ class Tables:
         itab = np.asarray(tables["itab"])
         self.flags = int(tables["flags"])
         self.af = np.asarray(tables["airfoils"]).reshape(-1, L.AF_STRIDE)
-        self.ac = np.asarray(ac_state).reshape(-1, L.AC_STRIDE)
+        self.ac = L.pad_ac_state(ac_state)
         v3 = lambda f: np.ascontiguousarray(tab[f:f + 3, :n].T)
         s1 = lambda f: np.ascontiguousarray(tab[f, :n])
         self.PC, self.P0, self.P1 = v3(L.F_PC), v3(L.F_P0), v3(L.F_P1)
@@ -69,6 +69,7 @@ class Tables:
         self.total_velocity = bool(self.flags & L.FLAG_TOTAL_VELOCITY)
         self.in_plane = bool(self.flags & L.FLAG_IN_PLANE)
         self.match_pro = bool(self.flags & L.FLAG_MATCH_MACHUP_PRO)
+        self.constrain_sheet = bool(self.flags & L.FLAG_CONSTRAIN_VORTEX_SHEET)
         # earth-fixed absolute positions, as the reference forms them (scene.py:445-447, 472-475)
         pos = self.ac[self.aircraft, L.AC_POS:L.AC_POS + 3]
         self.PC_abs = pos + self.PC
@@ -348,6 +349,12 @@ def flow_state(T):
     F.V_inf_and_rot = np.linalg.norm(F.v_inf_and_rot, axis=1)
     F.u_trailing_0 = j0 / np.linalg.norm(j0, axis=-1, keepdims=True)          # scene.py:591
     F.u_trailing_1 = j1 / np.linalg.norm(j1, axis=-1, keepdims=True)          # scene.py:592
+    if T.constrain_sheet:                                                     # scene.py:595-611
+        zf = ac[:, L.AC_ZF:L.AC_ZF + 3]                                       # body z axis of the owning aircraft, earth axes
+        for name in ("u_trailing_0", "u_trailing_1"):
+            u = getattr(F, name)
+            u = u - zf * np.einsum('ij,ij->i', zf, u)[:, None]                # (I - z z^T) u
+            setattr(F, name, u / np.linalg.norm(u, axis=-1, keepdims=True))
     if T.in_plane:                                                            # scene.py:637-643
         dot = np.einsum('ij,ij->i', T.US, F.v_inf)
         F.v_inf_in_plane = F.v_inf - T.US * dot[:, None]

@@ -17,7 +17,8 @@ def load(name):
     g = {k: z[k] for k in z.files}
     tables = {"tab": g["tab"], "itab": g["itab"], "airfoils": g["airfoils"], "n": int(g["n"]), "ld": int(g["ld"]),
               "n_aircraft": int(g["n_aircraft"]), "n_segments": int(g["n_segments"]), "flags": int(g["flags"])}
-    return tables, g["ac_state"], g, meta
+    from machupx_b200.layout import pad_ac_state
+    return tables, pad_ac_state(g["ac_state"]), g, meta
 
 
 def segment_sums(g, tables):

@@ -214,3 +214,34 @@ def test_lu_switchable_variants(env):
         assert out.returncode == 0, out.stderr[-2000:]
         res = json.loads(out.stdout.strip().splitlines()[-1])
         assert res["rel_residual"] < 1e-12, (env, res)
+
+
+def test_lu_pivot_guard_flags_matrices_the_unpivoted_factorisation_cannot_trust():
+    """the LU is unpivoted; a pivot six orders of magnitude below the largest raises LLS_STATUS_SMALL_PIVOT,
+    a zero pivot LLS_STATUS_NAN (LAPACK: singular), and a dominant matrix raises neither."""
+    from machupx_b200.device import DeviceScene
+    n = 200
+    ld = L.padded_ld(n)
+    tables = {"n": n, "ld": ld, "n_aircraft": 1, "n_segments": 1, "flags": L.FLAG_DEFAULT,
+              "tab": np.zeros((L.NF, ld)), "itab": np.zeros((L.NI, ld), dtype=np.int32), "airfoils": np.zeros((1, L.AF_STRIDE))}
+    dev = DeviceScene(tables)
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n, n)) / np.sqrt(n) + np.diag(5.0 + rng.random(n))
+    b = rng.standard_normal(n)
+
+    def status_after(mat):
+        dev.d_status.zero_()
+        x, _ = dev.lu_solve_dense(mat, b)
+        return dev.status(), x
+
+    st, x = status_after(A)
+    assert st & (L.STATUS_SMALL_PIVOT | L.STATUS_NAN) == 0
+    assert np.abs(A @ x - b).max() < 1e-12
+    tiny = A.copy()
+    tiny[137, 137] = 1e-9 + tiny[137, :137] @ np.linalg.solve(tiny[:137, :137], tiny[:137, 137])     # pivot 137 becomes ~1e-9
+    st, _ = status_after(tiny)
+    assert st & L.STATUS_SMALL_PIVOT
+    sing = A.copy()
+    sing[0, 0] = 0.0
+    st, _ = status_after(sing)
+    assert st & L.STATUS_NAN

@@ -193,3 +193,39 @@ def test_empty_scene_and_bad_requests_fail_like_the_reference():
     with pytest.raises(NotImplementedError):                   # batched stencils report body and wind frames only
         scene._batched_ok({"batched": True, "stab_frame": True})
     assert scene._batched_ok({}) is False and scene._batched_ok({"batched": True}) is True
+
+
+def test_table_revisions_drive_every_device_upload():
+    """table freshness is a revision counter, not object identity.  A control change bumps the revision and
+    re-uploads five flap rows; a pose change bumps the full revision and re-uploads everything (no GPU: a recording device)."""
+    from machupx_b200 import layout as L
+
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+
+        def upload_tables(self, tables):
+            self.calls.append("tables")
+
+        def upload_rows(self, tab, fields):
+            self.calls.append(("rows", tuple(fields), float(tab[L.F_FLAP_DEFL].max())))
+
+    scene = _scene()
+    dev = Recorder()
+    have = scene._upload_if_stale(dev, None)
+    assert dev.calls == ["tables"]
+    assert scene._upload_if_stale(dev, have) == have and dev.calls == ["tables"]          # nothing changed: nothing uploaded
+    scene.set_aircraft_control_state({"elevator": 4.0})
+    scene._refresh_tables()
+    assert scene._tables["tab"][L.F_FLAP_DEFL].max() == pytest.approx(np.radians(4.0))
+    have2 = scene._upload_if_stale(dev, have)
+    assert have2 != have and dev.calls[-1][0] == "rows" and dev.calls[-1][1] == L.FLAP_FIELDS
+    assert dev.calls[-1][2] == pytest.approx(np.radians(4.0))
+    other = Recorder()                                                                      # a second consumer that is two revisions behind
+    scene.set_aircraft_control_state({"elevator": -2.0})
+    scene._refresh_tables()
+    assert scene._upload_if_stale(other, have)[0] == scene._tables_rev and other.calls[-1][0] == "rows"
+    scene.set_aircraft_state({"position": [0.0, 0.0, -500.0], "velocity": 100.0, "alpha": 1.0})
+    scene._refresh_tables()
+    have3 = scene._upload_if_stale(dev, have2)
+    assert dev.calls[-1] == "tables" and have3[1] == have2[1] + 1

@@ -69,12 +69,13 @@ def test_reference_known_answers_nonlinear():
     """Hard-coded goldens of the reference's test_nonlinear_solver (test/scene_tests/test_solve_forces.py:114-122)."""
     tables, g, meta, res = _solve("testplane_nonlinear")
     total = _fm_from(res["seg_fm"], meta)["test_plane"]["total"]
-    gold = {"FL": 20.747215061024466, "FD": 1.3809910489999096, "FS": 0.0, "Fx": -0.6560930935409863,
-            "Fy": 0.0, "Fz": -20.782772428340866, "Mx": 0.0, "My": -12.65665591120846, "Mz": 0.0}
-    # values read from the reference's own assertions; checked below to 1e-10 like the reference does
+    # the constants the reference asserts (to 1e-10) in test/scene_tests/test_solve_forces.py:114-122
+    gold = {"FL": 20.959074770349314, "FD": 1.3934114313254868, "FS": 0.0, "Fx": -0.661101441894963,
+            "Fy": 0.0, "Fz": -20.994936425947238, "Mx": 0.0, "My": -12.873864820066961, "Mz": 0.0}
     ref_total = meta["FM"]["test_plane"]["total"]
-    for k in gold:
-        assert abs(total[k] - ref_total[k]) < 1e-10, k
+    for k, v in gold.items():
+        assert abs(total[k] - v) < 1e-10, (k, total[k], v)           # oracle vs the reference's hard-coded answer
+        assert abs(total[k] - ref_total[k]) < 1e-10, k                # oracle vs the fixture generated from the reference
 
 
 def test_circulation_golden_file_of_the_reference():
