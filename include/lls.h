@@ -191,6 +191,12 @@ int lls_bind(lls_scene* h, const double* d_tab, const int32_t* d_itab, const dou
 int lls_bind_batch(lls_scene* h, int ncases, const double* d_tab, const int32_t* d_itab, const double* d_airfoils,
                    double* d_out, double* d_vji, double* d_mat, void* d_work, size_t work_bytes_per_case, int32_t* d_ctl);
 
+/* Per-case copies of the double table: the cases of the bound batch read d_tab + case * case_stride_doubles (LLS_NF * ld
+ * doubles each) instead of one shared table, so a batch can also carry cases that differ in control deflections (the five flap
+ * rows), position or orientation (every earth-axes row): the stencils of control_derivatives (scene.py:2180), state_derivatives
+ * (:2276), pitch_trim (:2440).  The int table and the airfoils stay shared.  case_stride_doubles = 0 returns to one shared table. */
+int lls_set_case_tables(lls_scene* h, const double* d_tab, size_t case_stride_doubles);
+
 /* Newton iteration of every case of the bound batch in lock step; a case leaves the iteration when its residual norm
  * falls below `convergence` exactly as the reference's `while` test does (scene.py:853), so per-case iteration counts
  * equal those of separate solves.  Host outputs, ncases entries each. */

@@ -30,6 +30,7 @@ SIGNATURES = {
     "lls_destroy": (_i, [_vp]),
     "lls_bind": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t]),
     "lls_bind_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "lls_set_case_tables": (_i, [_vp, _vp, ctypes.c_size_t]),
     "lls_solve_nonlinear_batch": (_i, [_vp, _d, _d, _i, _vp, _pi, _pd, _pi]),
     "lls_get_status_batch": (_i, [_vp, _vp, _pi]),
     "lls_query_sizes_partitioned": (_i, [_i, _i, _i, ctypes.POINTER(Sizes)]),

@@ -15,6 +15,7 @@ namespace lls {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) linear_rows_kernel(int n, int ld, int flags, const double* __restrict__ tab, double* __restrict__ W,
                                                           CaseStrides cs) {
+    tab = case_ptr(tab, cs.tab);
     W = case_work_ptr(W, cs.work);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(int n, int ld, int flags,
                                                        const double* __restrict__ W, const double* __restrict__ V,
                                                        double* __restrict__ M, CaseStrides cs) {
     if (LLS_CASE_INACTIVE(cs)) return;
+    tab = case_ptr(tab, cs.tab);
     W = case_work_ptr(W, cs.work);
     V = case_ptr(V, cs.V);
     M = case_ptr(M, cs.M);
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int fl
                                                            double* __restrict__ out, double* __restrict__ partial, int vel_only,
                                                            int* __restrict__ status, CaseStrides cs) {
     if (LLS_CASE_INACTIVE(cs)) return;
+    tab = case_ptr(tab, cs.tab);
     V = case_ptr(V, cs.V);
     W = case_work_ptr(W, cs.work);
     out = case_ptr(out, cs.out);

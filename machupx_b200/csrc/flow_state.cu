@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
                                                         const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                         const double* __restrict__ ac, double* __restrict__ W,
                                                         double* __restrict__ out, int* __restrict__ status, CaseStrides cs) {
+    tab = case_ptr(tab, cs.tab);
     ac = case_ptr(ac, cs.ac);
     W = case_work_ptr(W, cs.work);
     out = case_ptr(out, cs.out);

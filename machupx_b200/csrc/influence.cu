@@ -134,6 +134,7 @@ constexpr int kInfUnroll = INF_UNROLL;   // rows per trip of the control-point l
 __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kernel(
     int n, int ld, const double* __restrict__ tab, const int32_t* __restrict__ itab, const double* __restrict__ ac,
     const double* __restrict__ out, double* __restrict__ V, double thr, int* __restrict__ status, CaseStrides cs) {
+    tab = case_ptr(tab, cs.tab);
     ac = case_ptr(ac, cs.ac);
     out = case_ptr(out, cs.out);
     V = case_ptr(V, cs.V);

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
                                                                 const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                                 const double* __restrict__ W, double* __restrict__ out,
                                                                 double* __restrict__ seg_fm, int* __restrict__ status, CaseStrides cs) {
+    tab = case_ptr(tab, cs.tab);
     status = case_work_ptr(status, cs.work);
     W = case_work_ptr(W, cs.work);
     out = case_ptr(out, cs.out);

@@ -194,6 +194,16 @@ extern "C" int lls_bind_batch(lls_scene* h, int ncases, const double* d_tab, con
     return LLS_OK;
 }
 
+extern "C" int lls_set_case_tables(lls_scene* h, const double* d_tab, size_t case_stride_doubles) {
+    LLS_REQUIRE(h != nullptr && d_tab != nullptr, LLS_ERR_ARG, "lls_set_case_tables: null argument");
+    LLS_REQUIRE(h->ctl != nullptr, LLS_ERR_STATE, "lls_set_case_tables: no batch bound (lls_bind_batch)");
+    LLS_REQUIRE(case_stride_doubles == 0 || case_stride_doubles >= (size_t)LLS_NF * h->ld, LLS_ERR_ARG,
+                "lls_set_case_tables: stride shorter than one table");
+    h->tab = d_tab;
+    h->cs.tab = case_stride_doubles;
+    return LLS_OK;
+}
+
 extern "C" int lls_set_state(lls_scene* h, const double* d_ac_state) {
     LLS_REQUIRE(h != nullptr && d_ac_state != nullptr, LLS_ERR_ARG, "lls_set_state: null argument");
     h->ac = d_ac_state;

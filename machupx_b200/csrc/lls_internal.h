@@ -64,6 +64,7 @@ enum WField {
 // buffer repeated with these element strides (all zero for a single scene).  `active` masks cases out of the Newton phase.
 struct CaseStrides {
     size_t out = 0, V = 0, M = 0, ac = 0, seg = 0;   // doubles
+    size_t tab = 0;                                   // doubles between the per-case copies of the double table (0: one table shared by every case)
     size_t work = 0;                                  // BYTES between the work regions of consecutive cases
     const int* active = nullptr;
     // row partition of ONE large scene over the GPUs of a box: 64-row blocks dealt round-robin, rank r owns global blocks

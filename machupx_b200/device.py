@@ -237,6 +237,23 @@ class BatchDeviceScene:
         for f in fields:
             self.d_tab[f].copy_(torch.from_numpy(np.ascontiguousarray(tab[f], dtype=np.float64)))
 
+    def upload_case_tables(self, case_tables):
+        """(ncases, NF, ld) per-case copies of the double table (cases that differ in control deflections or pose)."""
+        t = np.ascontiguousarray(case_tables, dtype=np.float64)
+        assert t.shape == (self.ncases, L.NF, self.ld), t.shape
+        if getattr(self, "d_tab_cases", None) is None:
+            self.d_tab_cases = torch.empty((self.ncases, L.NF, self.ld), dtype=torch.float64, device=self.device)
+        self.d_tab_cases.copy_(torch.from_numpy(t))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.lls_set_case_tables(self.handle, _ptr(self.d_tab_cases), ctypes.c_size_t(L.NF * self.ld)))
+        self._case_tables_on = True
+
+    def use_shared_tables(self):
+        if getattr(self, "_case_tables_on", False):
+            with torch.cuda.device(self.device):
+                _native.check(self.lib.lls_set_case_tables(self.handle, _ptr(self.d_tab), ctypes.c_size_t(0)))
+            self._case_tables_on = False
+
     def upload_states(self, ac_states):
         self.h_ac.copy_(torch.from_numpy(np.ascontiguousarray(L.pad_ac_state(np.asarray(ac_states, dtype=np.float64).reshape(self.ncases, self.n_aircraft, -1)))))
         self.d_ac.copy_(self.h_ac, non_blocking=True)

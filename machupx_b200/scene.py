@@ -509,9 +509,10 @@ class Scene:
             ap.angular_rate_frame = saved_frame
         return np.array(rows)
 
-    def _solve_batch_rows(self, ac_states, max_batch=4096):
+    def _solve_batch_rows(self, ac_states, max_batch=4096, case_tables=None):
         """Device part of a batch: ``ac_states`` (ncases, n_aircraft, AC_STRIDE) per-aircraft state blocks as build_aircraft_state
-        makes them, all for the geometry the scene currently has."""
+        makes them, all for the geometry the scene currently has -- or, with ``case_tables`` (ncases, NF, ld), every case with
+        its own copy of the double table (control deflections / pose differ between the cases)."""
         from .device import BatchDeviceScene
         from .forces import batch_totals
         n_total = len(ac_states)
@@ -531,7 +532,11 @@ class Scene:
                     or dev.n_segments != self._tables["n_segments"] or dev.n_aircraft != self._num_aircraft:
                 dev = self._batch_device = BatchDeviceScene(self._tables, nc)
                 self._batch_revs = (self._tables_rev, self._tables_full_rev)
-            self._batch_revs = self._upload_if_stale(dev, self._batch_revs)
+            if case_tables is None:
+                self._batch_revs = self._upload_if_stale(dev, self._batch_revs)
+                dev.use_shared_tables()
+            else:
+                dev.upload_case_tables(case_tables[lo:hi])
             dev.upload_states(ac_states[lo:hi])
             seg_fm[lo:hi], its[lo:hi], err[lo:hi], status[lo:hi] = dev.solve(
                 self._solver_type, self._solver_convergence, self._solver_relaxation, self._max_solver_iterations,
@@ -543,7 +548,7 @@ class Scene:
                                 float(err[~converged].max()) if not converged.all() else 0.0)
         except Exception as e:
             self._handle_error(e)
-        return {"totals": batch_totals(seg_fm, ac_states, info), "iterations": its, "final_error": err, "converged": converged,
+        return {"totals": batch_totals(seg_fm, ac_states, info) if case_tables is None else None, "iterations": its, "final_error": err, "converged": converged,
                 "status": status, "seg_fm": seg_fm}
 
     def _report_status(self, status, err):
@@ -646,10 +651,9 @@ class Scene:
             sub = dict(kwargs)
             sub["aircraft"] = name
             sub.pop("filename", None)
-            seq = {k: v for k, v in sub.items() if k != "batched"}      # flap deflections live in the shared tables: sequential
             derivs[name] = {"stability": self.stability_derivatives(**sub)[name],
                             "damping": self.damping_derivatives(**sub)[name],
-                            "control": self.control_derivatives(**seq)[name]}
+                            "control": self.control_derivatives(**sub)[name]}
         filename = kwargs.get("filename", None)
         if filename is not None:
             with open(filename, "w") as handle:
@@ -661,32 +665,59 @@ class Scene:
         self.solve_forces(dimensional=False, **kw)
         return self._FM
 
-    def _stencil_totals(self, name, setters):
-        """Totals of a finite-difference stencil as ONE batched device pass: every callable of
-        ``setters`` perturbs the airplane ``name`` starting from its current state (velocity / angular rates only: the
-        geometry tables are shared by the cases); returns one {key: float} dictionary of aircraft totals per case, with the
-        body- and wind-frame keys of ``_FM[name]["total"]``."""
+    def _stencil_totals(self, name, setters, opts=None):
+        """Totals of a finite-difference stencil as ONE batched device pass.  Every callable of
+        ``setters`` perturbs the airplane ``name`` starting from its current state: velocity, angular rates, control deflections,
+        position or orientation.  Cases that only change the flight state share the geometry tables; as soon as one case changes
+        control deflections or pose, every case gets its own copy of the double table (lls_set_case_tables).  Returns one
+        {key: float} dictionary of aircraft totals per case, laid out like ``_FM[name]["total"]`` for the frames / dimensional
+        switches in ``opts``.  The airplane and the host tables are left as they were."""
         ap = self._airplanes[name]
         self._refresh_tables()
-        saved = ap.get_state()
-        rows = []
+        base_revs = (self._tables_rev, self._tables_full_rev)
+        base_tab = self._tables["tab"]
+        saved = tuple(np.copy(x) for x in ap.get_state())
+        saved_controls = copy.deepcopy(ap.current_control_state)
+        saved_frame = ap.angular_rate_frame
+
+        def restore():
+            ap.v, ap.w, ap.p_bar, ap.q = (np.copy(x) for x in saved)
+            ap.angular_rate_frame = saved_frame
+            if ap.current_control_state != saved_controls:
+                ap.set_control_state(saved_controls)
+
+        rows, tabs, frames = [], [], []
         try:
             for perturb in setters:
+                restore()
                 perturb(ap)
+                self._refresh_tables()
                 rows.append(build_aircraft_state(self))
-                ap.v, ap.w, ap.p_bar, ap.q = (np.copy(x) for x in saved)
+                changed = (self._tables_rev, self._tables_full_rev) != base_revs or self._tables["tab"] is not base_tab
+                tabs.append(self._tables["tab"].copy() if changed else None)
+                frames.append(self._frames())
         finally:
-            ap.v, ap.w, ap.p_bar, ap.q = saved
-        tot = self._solve_batch_rows(np.array(rows))["totals"][name]
-        return [{k: float(v[i]) for k, v in tot.items()} for i in range(len(setters))]
+            restore()
+            self._refresh_tables()
+        if any(t is not None for t in tabs):
+            here = self._tables["tab"]
+            tabs = np.array([here if t is None else t for t in tabs])
+        else:
+            tabs = None
+        res = self._solve_batch_rows(np.array(rows), case_tables=tabs)
+        kwargs = dict(opts or {})
+        body, stab, wind = self._get_frames(**kwargs)
+        out = []
+        for i in range(len(setters)):
+            fm = assemble_fm(res["seg_fm"][i], frames[i], non_dimensional=kwargs.get("non_dimensional", True),
+                             dimensional=kwargs.get("dimensional", True), body_frame=body, stab_frame=stab, wind_frame=wind)
+            out.append(fm[name]["total"])
+        return out
 
     def _batched_ok(self, kwargs):
-        """``batched=True`` runs a derivative stencil as one batch; the stability-frame keys are not part of the batch totals."""
-        if not kwargs.get("batched", False):
-            return False
-        if self._get_frames(**kwargs)[1]:
-            raise NotImplementedError("batched derivative stencils report the body and wind frames; use stab_frame=False")
-        return True
+        """``batched=True``: the driver's finite-difference stencil runs as one batched device pass instead of one solve per
+        stencil point."""
+        return bool(kwargs.get("batched", False))
 
     def stability_derivatives(self, **kwargs):
         derivs = {}                                                            # scene.py:1876-1994
@@ -702,7 +733,7 @@ class Scene:
                     lambda a: a.set_aerodynamic_state(alpha=alpha_0 + dtheta),
                     lambda a: a.set_aerodynamic_state(alpha=alpha_0 - dtheta),
                     lambda a: a.set_aerodynamic_state(alpha=alpha_0, beta=beta_0 + dtheta),
-                    lambda a: a.set_aerodynamic_state(alpha=alpha_0, beta=beta_0 - dtheta)])
+                    lambda a: a.set_aerodynamic_state(alpha=alpha_0, beta=beta_0 - dtheta)], dict(kwargs, dimensional=False))
                 scale = 1 / (2 * np.radians(dtheta))
                 d = {}
                 for k in keys:
@@ -751,7 +782,7 @@ class Scene:
             if batched:
                 def rate(dw):
                     return lambda a: setattr(a, "w", omega_0 + dw)
-                tot = self._stencil_totals(name, [rate(sgn * p) for p in perts for sgn in (1.0, -1.0)])
+                tot = self._stencil_totals(name, [rate(sgn * p) for p in perts for sgn in (1.0, -1.0)], dict(kwargs, dimensional=False))
                 pairs = [(tot[2 * i], tot[2 * i + 1]) for i in range(3)]
             else:
                 for p in perts:
@@ -776,11 +807,28 @@ class Scene:
         derivs = {}                                                            # scene.py:2180-2273
         keys, _ = self._frame_keys(**kwargs)
         dtheta = kwargs.get("dtheta", 0.5)
+        batched = self._batched_ok(kwargs)
+        kwargs = {k: v for k, v in kwargs.items() if k != "batched"}
         for name in self._get_aircraft(**kwargs):
             ap = self._airplanes[name]
             current = copy.deepcopy(ap.current_control_state)
             pert = copy.deepcopy(current)
             d = {}
+            if batched:      # 2 x n_controls cases, each with its own flap rows, in one device pass
+                def deflect(control, delta):
+                    def perturb(a):
+                        moved = copy.deepcopy(current)
+                        moved[control] = current.get(control, 0.0) + delta
+                        a.set_control_state(control_state=moved)
+                    return perturb
+                tot = self._stencil_totals(name, [deflect(c, sgn * dtheta) for c in ap.control_names for sgn in (1.0, -1.0)],
+                                           dict(kwargs, dimensional=False))
+                diff = 2 * np.radians(dtheta)
+                for i, control in enumerate(ap.control_names):
+                    for k in keys:
+                        d[k + ",d" + control] = (tot[2 * i][k] - tot[2 * i + 1][k]) / diff
+                derivs[name] = d
+                continue
             for control in ap.control_names:
                 value = current.get(control, 0.0)
                 pert[control] = value + dtheta
@@ -806,18 +854,50 @@ class Scene:
                 ("position", "x_f", 0, dx), ("position", "y_f", 1, dx), ("position", "z_f", 2, dx),
                 ("angular_rates", "p", 0, dw), ("angular_rates", "q", 1, dw), ("angular_rates", "r", 2, dw),
                 ("orientation", "qx", 0, de), ("orientation", "qy", 1, de), ("orientation", "qz", 2, de)]
+        batched = self._batched_ok(kwargs)
+        kwargs = {k: v for k, v in kwargs.items() if k != "batched"}
         for name in self._get_aircraft(**kwargs):
             ap = self._airplanes[name]
             v0, w0, p0, q0 = ap.get_state()
             orig = {"position": np.asarray(p0, dtype=float), "velocity": earth_to_body(q0, v0 - self._get_wind(p0)),
                     "orientation": q0, "angular_rates": np.asarray(w0, dtype=float)}
             d = {}
+            if batched:      # the 24 stencil points (12 of them move or rotate the aircraft: per-case tables) in one device pass
+                setters = []
+                for variable, tag, index, step in plan:
+                    setters += self._state_stencil(variable, index, step, orig)
+                tot = self._stencil_totals(name, setters, {k: v for k, v in kwargs.items() if k != "filename"})
+                for i, (variable, tag, index, step) in enumerate(plan):
+                    f, b = tot[2 * i], tot[2 * i + 1]
+                    d.update({"d{0},d{1}".format(k, tag): (f[k] - b[k]) * 0.5 / step for k in ("Fx", "Fy", "Fz", "Mx", "My", "Mz")})
+                derivs[name] = d
+                continue
             for variable, tag, index, step in plan:
                 d.update(self._determine_state_derivs(variable, tag, index, step, orig, name, **kwargs))
             derivs[name] = d
             ap.set_state(**orig)
             self._solved = False
         return derivs
+
+    @staticmethod
+    def _state_stencil(variable, index, perturbation, orig_state):
+        """The forward and backward perturbation of one state variable as setters for ``_stencil_totals``: exactly the states
+        ``_determine_state_derivs`` solves one after the other (scene.py:2372-2437)."""
+        def setter(pert):
+            return lambda a: a.set_state(**pert)
+        fwd, bwd = copy.deepcopy(orig_state), copy.deepcopy(orig_state)
+        if variable in ("position", "velocity", "angular_rates"):
+            fwd[variable][index] += perturbation
+            bwd[variable][index] += perturbation
+            bwd[variable][index] -= 2.0 * perturbation
+        else:
+            dq = np.array([1.0, 0.0, 0.0, 0.0])
+            dq[index + 1] = 0.5 * perturbation
+            dq = dq / np.linalg.norm(dq)
+            q0, v0 = orig_state["orientation"], orig_state["velocity"]
+            fwd["orientation"], fwd["velocity"] = quat_product(q0, dq), earth_to_body(dq, v0)
+            bwd["orientation"], bwd["velocity"] = quat_product(q0, quat_conjugate(dq)), body_to_earth(dq, v0)
+        return [setter(fwd), setter(bwd)]
 
     def _determine_state_derivs(self, variable, tag, index, perturbation, orig_state, aircraft_name, **kwargs):
         ap = self._airplanes[aircraft_name]                                    # scene.py:2372-2437
@@ -892,11 +972,40 @@ class Scene:
         J = np.zeros((2, 2))
         it = 0
         alpha_new, flap_new = alpha, flap
+        batched = self._batched_ok(kwargs)
         while (abs(R) > 1e-10).any():
             step = 0.5
             here = copy.deepcopy(ap.current_control_state)
             pert = copy.deepcopy(here)
             value = here.get(control, 0.0)
+            if batched:      # the four Jacobian solves of this Newton step in one device pass
+                alpha_0, beta_0, _ = ap.get_aerodynamic_state()
+
+                def deflect(delta):
+                    def perturb(a):
+                        moved = copy.deepcopy(here)
+                        moved[control] = value + delta
+                        a.set_control_state(control_state=moved)
+                    return perturb
+                c_f, c_b, a_f, a_b = self._stencil_totals(name, [deflect(step), deflect(-step),
+                                                                 lambda a: a.set_aerodynamic_state(alpha=alpha_0 + step),
+                                                                 lambda a: a.set_aerodynamic_state(alpha=alpha_0 - step)], opts)
+                diff = 2 * np.radians(step)
+                J[0, 1], J[1, 1] = (c_f["CL"] - c_b["CL"]) / diff, (c_f["Cm_w"] - c_b["Cm_w"]) / diff
+                J[0, 0], J[1, 0] = (a_f["CL"] - a_b["CL"]) / diff, (a_f["Cm_w"] - a_b["Cm_w"]) / diff
+                delta = np.linalg.solve(J, -R)
+                alpha_new = alpha + np.degrees(delta[0]) * relax
+                ap.set_aerodynamic_state(alpha=alpha_new)
+                flap_new = flap + np.degrees(delta[1]) * relax
+                controls[control] = flap_new
+                ap.set_control_state(controls)
+                alpha, flap = alpha_new, flap_new
+                R = self._get_aircraft_pitch_trim_residuals(name, CL_des, Cm_des)
+                if verbose: print("{0:<20}{1:<20}{2:<25}{3:<25}".format(alpha, flap, R[0], R[1]))
+                it += 1
+                if it == max_iter:
+                    raise MaxIterationError("pitch_trim", np.max(np.abs(R)))
+                continue
             pert[control] = value + step
             ap.set_control_state(control_state=pert)
             fwd = self.solve_forces(**opts)[name]["total"]
@@ -971,8 +1080,38 @@ class Scene:
         it = 0
         J = np.zeros((2, 2))
         pert = copy.copy(controls_original)
+        batched = self._batched_ok(kwargs)
         while (abs(R) > 1e-10).any():
             step = 0.001
+            if batched:      # two control and two elevation-angle perturbations (the latter rotate the aircraft) in one device pass
+                def deflect(delta, base=copy.copy(pert), value=flap):
+                    def perturb(a):
+                        moved = copy.copy(base)
+                        moved[control] = value + delta
+                        a.set_control_state(control_state=moved)
+                    return perturb
+
+                def elevate(th):
+                    q_t, v_t = pose(th)
+                    return lambda a: a.set_state(position=p_orig, velocity=v_t, orientation=q_t, angular_rates=w_orig)
+                c_f, c_b, t_f, t_b = self._stencil_totals(name, [deflect(step), deflect(-step), elevate(theta + step),
+                                                                 elevate(theta - step)], dict(dimensional=False))
+                J[0, 1], J[1, 1] = (c_f["CL"] - c_b["CL"]) / (2.0 * step), (c_f["Cm"] - c_b["Cm"]) / (2.0 * step)
+                J[0, 0], J[1, 0] = (t_f["CL"] - t_b["CL"]) / (2.0 * step), (t_f["Cm"] - t_b["Cm"]) / (2.0 * step)
+                delta = np.linalg.solve(J, -R)
+                theta += delta[0] * relax
+                flap += delta[1] * relax
+                q_n, v_n = pose(theta)
+                curr_state = {"position": list(p_orig), "velocity": list(v_n), "orientation": list(q_n), "angular_rates": list(w_orig)}
+                ap.set_state(**curr_state)
+                pert[control] = flap
+                ap.set_control_state(pert)
+                R = self._get_aircraft_pitch_trim_residuals(name, CL_des, Cm_des)
+                if verbose: print("{0:<20}{1:<20}{2:<25}{3:<25}".format(math.degrees(theta), flap, R[0], R[1]))
+                it += 1
+                if it == max_iter:
+                    raise MaxIterationError("pitch_trim_using_orientation", np.max(np.abs(R)))
+                continue
             pert[control] = flap + step
             ap.set_control_state(control_state=pert)
             fwd = self.solve_forces(dimensional=False)[name]["total"]
@@ -1027,15 +1166,22 @@ class Scene:
             if verbose: print("Calculating the aerodynamic center for {0}...".format(name))
             ap = self._airplanes[name]
             v_wind = self._get_wind(ap.p_bar)
-            mid = self.solve_forces(dimensional=False)[name]["total"]
-            a0, B0, V0 = ap.get_aerodynamic_state(v_wind=v_wind)
             h = 0.5
-            ap.set_aerodynamic_state(alpha=a0 - h, beta=B0, velocity=V0, v_wind=v_wind)
-            lo = self.solve_forces(dimensional=False)[name]["total"]
-            ap.set_aerodynamic_state(alpha=a0 + h, beta=B0, velocity=V0, v_wind=v_wind)
-            hi = self.solve_forces(dimensional=False)[name]["total"]
-            ap.set_aerodynamic_state(alpha=a0, beta=B0, velocity=V0, v_wind=v_wind)
-            self._solved = False
+            if self._batched_ok(kwargs):      # the three angles of attack of the second-difference stencil in one device pass
+                a0, B0, V0 = ap.get_aerodynamic_state(v_wind=v_wind)
+                mid, lo, hi = self._stencil_totals(name, [
+                    lambda a: None,
+                    lambda a: a.set_aerodynamic_state(alpha=a0 - h, beta=B0, velocity=V0, v_wind=v_wind),
+                    lambda a: a.set_aerodynamic_state(alpha=a0 + h, beta=B0, velocity=V0, v_wind=v_wind)], dict(dimensional=False))
+            else:
+                mid = self.solve_forces(dimensional=False)[name]["total"]
+                a0, B0, V0 = ap.get_aerodynamic_state(v_wind=v_wind)
+                ap.set_aerodynamic_state(alpha=a0 - h, beta=B0, velocity=V0, v_wind=v_wind)
+                lo = self.solve_forces(dimensional=False)[name]["total"]
+                ap.set_aerodynamic_state(alpha=a0 + h, beta=B0, velocity=V0, v_wind=v_wind)
+                hi = self.solve_forces(dimensional=False)[name]["total"]
+                ap.set_aerodynamic_state(alpha=a0, beta=B0, velocity=V0, v_wind=v_wind)
+                self._solved = False
             CA_a = (-hi["Cx"] + lo["Cx"]) / (2.0 * h)
             CN_a = (-hi["Cz"] + lo["Cz"]) / (2.0 * h)
             Cm_a = (hi["Cm"] - lo["Cm"]) / (2.0 * h)
@@ -1079,11 +1225,17 @@ class Scene:
         res = abs(CL - CL_target)
         if verbose: print("{0:<25}{1:<25}".format(alpha, CL))
         it = 0
+        batched = self._batched_ok(kwargs)
         while res > 1e-10:
-            ap.set_aerodynamic_state(alpha=alpha + 0.005)
-            CL_fwd = self.solve_forces(dimensional=False)[name]["total"]["CL"]
-            ap.set_aerodynamic_state(alpha=alpha - 0.005)
-            CL_bwd = self.solve_forces(dimensional=False)[name]["total"]["CL"]
+            if batched:      # both finite-difference solves of this secant step in one device pass
+                f, b = self._stencil_totals(name, [lambda a: a.set_aerodynamic_state(alpha=alpha + 0.005),
+                                                   lambda a: a.set_aerodynamic_state(alpha=alpha - 0.005)], dict(dimensional=False))
+                CL_fwd, CL_bwd = f["CL"], b["CL"]
+            else:
+                ap.set_aerodynamic_state(alpha=alpha + 0.005)
+                CL_fwd = self.solve_forces(dimensional=False)[name]["total"]["CL"]
+                ap.set_aerodynamic_state(alpha=alpha - 0.005)
+                CL_bwd = self.solve_forces(dimensional=False)[name]["total"]["CL"]
             alpha += (CL_target - CL) / ((CL_fwd - CL_bwd) / 0.01) * relax
             ap.set_aerodynamic_state(alpha=alpha)
             CL = self.solve_forces(dimensional=False)[name]["total"]["CL"]
@@ -1178,4 +1330,91 @@ class Scene:
     def _out_of_scope(self, *args, **kwargs):
         raise NotImplementedError("plotting / CAD / simulator-model export is outside the lifting-line solve path this package implements")
 
-    display_wireframe = display_planform = export_stl = export_vtk = export_stp = export_dxf = export_pylot_model = out_gamma = _out_of_scope
+    display_wireframe = display_planform = export_stl = export_vtk = export_stp = export_dxf = out_gamma = _out_of_scope
+
+    # ------------------------------------------------------------------------------------------------------
+    # linearised model for the Pylot simulator: 59 solves of the hot path (scene.py:3521-3747)
+    # ------------------------------------------------------------------------------------------------------
+    def export_pylot_model(self, **kwargs):
+        """Linearised coefficient model of the single aircraft of the scene (reference solve, all derivatives, a 21-point
+        drag polar in alpha and one in beta).  ``batched=True`` runs the derivative stencils and the two 21-state sweeps as
+        batched device passes.  Sets the aircraft to zero aerodynamic angles and zero control deflections, like the reference.
+        Returns the model dictionary (the reference only writes the file)."""
+        names = list(self._airplanes.keys())
+        if len(names) != 1:
+            raise IOError("export_pylot_model() may not be used when there is more than one aircraft in the scene.")
+        name = names[0]
+        ap = self._airplanes[name]
+        batched = self._batched_ok(kwargs)
+        model = copy.deepcopy(ap._input_dict)
+        model.pop("wings")
+        model.pop("airfoils")
+        model["units"] = self._unit_sys
+        model["CG"] = np.asarray(ap.CG).tolist()
+        model["weight"] = float(ap.W)
+        model["reference"] = {"area": float(ap.S_w), "longitudinal_length": float(ap.l_ref_lon), "lateral_length": float(ap.l_ref_lat)}
+        if "inertia" not in model:
+            model["inertia"] = kwargs.get("inertia", {k: "PLEASE SPECIFY" for k in ("Ixx", "Iyy", "Izz", "Ixy", "Ixz", "Iyz")})
+        if "angular_momentum" not in model:
+            model["angular_momentum"] = list(kwargs.get("angular_momentum", [0.0, 0.0, 0.0]))
+        controller = kwargs.get("controller_type", None)
+        for value in model.get("controls", {}).values():
+            if controller in ("keyboard", "joystick", None):
+                if "max_deflection" not in value and controller is None:
+                    value["max_deflection"] = "PLEASE SPECIFY"
+                value["input_axis"] = value.get("input_axis", "PLEASE SPECIFY")
+            if controller in ("time_sequence", None):
+                value["column_index"] = value.get("column_index", "PLEASE SPECIFY")
+        model["aero_model"] = {"type": "linearized_coefficients"}
+        for key in ("stall_angle_of_attack", "stall_sideslip_angle"):
+            if key in kwargs:
+                model["aero_model"][key] = kwargs[key]
+
+        V_ref = kwargs.get("velocity", 100)
+        self.set_aircraft_state(state={"velocity": V_ref})
+        self.set_aircraft_control_state()
+        FM_ref = self.solve_forces(dimensional=False)
+        derivs = self.derivatives(batched=batched)[name]
+        co = model["coefficients"] = {}
+        co["CL0"] = float(FM_ref[name]["total"]["CL"])
+        co["Cm0"] = float(FM_ref[name]["total"]["Cm"])
+        for key in ("CL,a", "Cm,a", "CS,b", "Cl,b", "Cn,b"):
+            co[key] = float(derivs["stability"][key])
+        for coef, rate in (("CS", "p"), ("Cl", "p"), ("Cn", "p"), ("CL", "q"), ("CD", "q"), ("Cm", "q"), ("CS", "r"), ("Cl", "r"), ("Cn", "r")):
+            co["{0},{1}_bar".format(coef, rate)] = float(derivs["damping"]["{0},{1}bar".format(coef, rate)])
+        unknown = 0.0 if kwargs.get("set_accel_derivs", False) else "PLEASE SPECIFY"
+        for key in ("CL,a_hat", "CD,a_hat", "Cm,a_hat", "CS,b_hat", "Cl,b_hat", "Cn,b_hat"):
+            co[key] = unknown
+        for control in ap.control_names:
+            co[control] = {k: float(derivs["control"]["{0},d{1}".format(k, control)]) for k in ("CL", "CD", "CS", "Cl", "Cm", "Cn")}
+
+        def sweep(states, keys):
+            if batched:
+                tot = self.solve_forces_batch([dict(st, position=[float(x) for x in ap.p_bar], velocity=float(V_ref)) for st in states])["totals"][name]
+                return [np.array(tot[k], dtype=float) for k in keys]
+            vals = [[] for _ in keys]
+            for st in states:
+                self.set_aircraft_state(state=dict(st, velocity=V_ref))
+                tot = self.solve_forces(dimensional=False, body_frame=False)[name]["total"]
+                for v, k in zip(vals, keys):
+                    v.append(tot[k])
+            return [np.array(v) for v in vals]
+
+        alphas = np.linspace(-10, 10, 21)
+        CL, CD = sweep([{"alpha": float(a)} for a in alphas], ("CL", "CD"))
+        fit = np.polyfit(CL, CD, 2)
+        co["CD0"], co["CD1"], co["CD2"] = float(fit[2]), float(fit[1]), float(fit[0])
+        line = np.polyfit(alphas, CL, 1)
+        a_L0 = -line[1] / line[0]
+        betas = np.linspace(-10, 10, 21)
+        CS, CD = sweep([{"alpha": float(a_L0), "beta": float(b)} for b in betas], ("CS", "CD"))
+        co["CD3"] = float(np.polyfit(CS, CD, 2)[0])
+        if batched:      # the sequential sweep leaves the aircraft at the last state it solved
+            self.set_aircraft_state(state={"velocity": V_ref, "alpha": float(a_L0), "beta": float(betas[-1])})
+        model["engines"] = model.get("engines", {"placeholder_engine": {}})
+        model["landing_gear"] = model.get("landing_gear", {"placeholder_landing_gear": {}})
+        filename = kwargs.get("filename", name + "_linearized.json")
+        if filename is not None:
+            with open(filename, "w") as handle:
+                json.dump(model, handle, indent=4)
+        return model

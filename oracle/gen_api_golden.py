@@ -39,6 +39,37 @@ def jsonable(x):
     return x
 
 
+def c3_golden():
+    """BASELINE.json configs[2] on the 8 x 8 sub-grid S.C3_SUB of the 64 x 64 alpha / beta grid: the reference's serial
+    set_aircraft_state -> solve_forces loop (scene.py:1535-1598) on examples/FlyingWing, linear (as shipped) and nonlinear
+    (default relaxation), with the Newton iteration count of every case read from the verbose printout."""
+    import contextlib
+    import io
+    import numpy as np
+    d = os.path.join(REF, "examples/FlyingWing")
+    inp = _embed(_load_json(os.path.join(d, "flying_wing_input.json")), d)
+    inp.pop("run", None)
+    res = {"input": inp, "alpha_idx": list(S.C3_SUB), "beta_idx": list(S.C3_SUB)}
+    states = S.c3_states(S.C3_SUB, S.C3_SUB)
+    for solver in ("linear", "nonlinear"):
+        cfg = json.loads(json.dumps(inp))
+        cfg["solver"]["type"] = solver
+        cfg["solver"].pop("relaxation", None)
+        scene = MX.Scene(cfg)
+        name = list(scene._airplanes.keys())[0]
+        totals, its = [], []
+        for st in states:
+            scene.set_aircraft_state(state=dict(st), aircraft=name)
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                FM = scene.solve_forces(verbose=True)
+            its.append(sum(1 for line in buf.getvalue().splitlines() if len(line.split()) == 2 and line.split()[0].isdigit()))
+            totals.append(FM[name]["total"])
+        res[solver] = {"totals": jsonable(totals), "iterations": its, "aircraft": name}
+        print("c3", solver, "iterations", min(its), "-", max(its), "CL", totals[0]["CL"], "..", totals[-1]["CL"])
+    return res
+
+
 def main():
     warnings.simplefilter("ignore")
     os.chdir(REF)
@@ -64,6 +95,9 @@ def main():
     for sep in (25, 10000):
         out["two_aircraft"][str(sep)] = jsonable(S.two_aircraft_case(MX.Scene, base, sep))
     out["distributions"] = jsonable(S.distributions_case(MX.Scene, base))
+    out["pylot"] = jsonable(S.pylot_case(MX.Scene, base, "/tmp/_pylot_ref.json"))
+    print("pylot", out["pylot"]["coefficients"]["CD0"])
+    out["c3"] = c3_golden()
     os.chdir(ROOT)
     with open(os.path.join(ROOT, "tests/golden/input_for_testing_embedded.json"), "w") as fh:
         json.dump(base, fh, indent=1)

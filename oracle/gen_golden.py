@@ -82,6 +82,17 @@ def _cases():
     wing = c["scene"]["aircraft"]["test_plane"]["file"]["wings"]["main_wing"]
     wing["airfoil"] = [[0.0, "NACA_0010"], [0.5, "NACA_2410"], [1.0, "NACA_4410"]]
     cases["testplane_airfoil_dist"] = c
+    # trailing vortex sheet constrained to the aircraft's x-y plane (scene.py:595-611) on a banked, pitched, yawed, rotating aircraft
+    c = copy.deepcopy(base)
+    c["scene"]["aircraft"]["test_plane"]["state"] = {"position": [0, 0, 1000], "angular_rates": [0.1, 0.05, 0.02], "velocity": 100,
+                                                     "alpha": 4.0, "beta": 3.0, "orientation": [20.0, 8.0, 30.0]}
+    c["solver"]["constrain_vortex_sheet"] = True
+    # tail raised out of the wing's x-y plane: with the sheet confined to that plane the main wing's trailing legs would otherwise
+    # graze the tail's control points, and the reference's own V_ji is then only reproducible to ~1e-7 (near-impingement)
+    wings = c["scene"]["aircraft"]["test_plane"]["file"]["wings"]
+    wings["h_stab"]["connect_to"]["dz"] = -0.5
+    wings["v_stab"]["connect_to"]["dz"] = -0.6
+    cases["testplane_constrained_sheet"] = c
     # ---- examples/Traditional (C1: linear, N = 200) ------------------------------------------------
     d = os.path.join(REF, "examples/Traditional")
     c = _embed(_load_json(os.path.join(d, "traditional_input.json")), d)

@@ -59,6 +59,14 @@ SOLVE_CASES = {
                              solver_opts={"match_machup_pro": True}),
     "kuchemann_offset": dict(solver="nonlinear", wings={"main_wing": {"sweep": 30.0, "ll_offset": "kuchemann"}}),
     "previous_guess": dict(solver="nonlinear", state=BASE_STATE, controls=NO_CONTROLS),
+    # scene.py:595-611: trailing directions projected into the aircraft's x-y plane (banked, pitched, yawed and rotating aircraft so
+    # that the body z axis is nowhere near an earth axis and the joints move with different velocities; tail raised out of the
+    # wing plane, otherwise the confined sheet grazes the tail's control points and the case is near-impingement)
+    "constrain_vortex_sheet": dict(solver="nonlinear", state=dict(BASE_STATE, alpha=4.0, beta=3.0, angular_rates=[0.1, 0.05, 0.02],
+                                                                  orientation=[20.0, 8.0, 30.0]),
+                                   wings={"h_stab": {"connect_to": {"ID": 1, "location": "root", "dx": -3.0, "dz": -0.5}},
+                                          "v_stab": {"connect_to": {"ID": 1, "location": "root", "dx": -3.0, "dz": -0.6}}},
+                                   solver_opts={"constrain_vortex_sheet": True}),
 }
 
 
@@ -75,35 +83,36 @@ def solve_case(Scene, base, name):
 
 
 # ---- test/scene_tests/test_derivatives.py ---------------------------------------------------------------------
-def derivatives_case(Scene, base, which):
+def derivatives_case(Scene, base, which, **kw):
+    """``kw``: extra keyword arguments of this package's drivers (batched=True); the reference is called without any."""
     scene = Scene(copy.deepcopy(base))
     if which == "stability":
-        return scene.stability_derivatives()                 # :9-33
+        return scene.stability_derivatives(**kw)             # :9-33
     if which == "damping":
-        return scene.damping_derivatives()                   # :36-69
+        return scene.damping_derivatives(**kw)               # :36-69
     if which == "control":
-        return scene.control_derivatives()                   # :72-106
+        return scene.control_derivatives(**kw)               # :72-106
     if which == "all":
-        return scene.derivatives(stab_frame=True)            # :109-160 (plus the stability frame)
+        return scene.derivatives(stab_frame=True, **kw)      # :109-160 (plus the stability frame)
     if which == "state":
-        return scene.state_derivatives()
+        return scene.state_derivatives(**kw)
     raise KeyError(which)
 
 
 # ---- test/scene_tests/test_other_methods.py ----------------------------------------------------------------------
-def other_case(Scene, base, which):
+def other_case(Scene, base, which, **kw):
     scene = Scene(_with(base, state=BASE_STATE, controls=NO_CONTROLS))
     if which == "target_CL":
-        return {"alpha": scene.target_CL(CL=0.5)}            # :11-35
+        return {"alpha": scene.target_CL(CL=0.5, **kw)}      # :11-35
     if which == "pitch_trim":
-        return scene.pitch_trim()                            # :38-63
+        return scene.pitch_trim(**kw)                        # :38-63
     if which == "pitch_trim_finite_moment":
-        return scene.pitch_trim(CL=0.1, Cm=0.2)              # :66-91
+        return scene.pitch_trim(CL=0.1, Cm=0.2, **kw)        # :66-91
     if which == "pitch_trim_orientation":
-        state, controls = scene.pitch_trim_using_orientation(CL=0.1, Cm=0.2)   # :94-122
+        state, controls = scene.pitch_trim_using_orientation(CL=0.1, Cm=0.2, **kw)   # :94-122
         return {"state": {k: [float(x) for x in v] for k, v in state.items()}, "controls": controls}
     if which == "aero_center":
-        return scene.aero_center()
+        return scene.aero_center(**kw)
     if which == "MAC":
         return scene.MAC()
     raise KeyError(which)
@@ -130,3 +139,25 @@ def distributions_case(Scene, base):
     scene = Scene(copy.deepcopy(base))
     dist = scene.distributions()
     return {ac: {seg: {k: [float(x) for x in v] for k, v in cols.items()} for seg, cols in segs.items()} for ac, segs in dist.items()}
+
+
+# ---- Scene.export_pylot_model (scene.py:3521-3747): 59 solves, no reference test; pinned by running the reference ------------------
+def pylot_case(Scene, base, filename, **kw):
+    """The linearised model as the file the call writes (the reference returns nothing)."""
+    import json
+    scene = Scene(_with(base, state=BASE_STATE, controls=NO_CONTROLS))
+    scene.export_pylot_model(filename=filename, set_accel_derivs=True, stall_angle_of_attack=15.0, **kw)
+    with open(filename) as fh:
+        return json.load(fh)
+
+
+# ---- BASELINE.json configs[2]: alpha / beta sweep of examples/FlyingWing (SURVEY.md section 8d "C3") ---------------------------------
+C3_ALPHAS = np.linspace(-2.0, 10.0, 64)
+C3_BETAS = np.linspace(-6.0, 6.0, 64)
+C3_SUB = (0, 9, 18, 27, 36, 45, 54, 63)          # the 8 x 8 sub-grid the reference is run on for the golden
+
+
+def c3_states(alpha_idx=None, beta_idx=None):
+    ai = range(64) if alpha_idx is None else alpha_idx
+    bi = range(64) if beta_idx is None else beta_idx
+    return [{"velocity": 100.0, "alpha": float(C3_ALPHAS[a]), "beta": float(C3_BETAS[b])} for a in ai for b in bi]

@@ -7,6 +7,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 CASES = ["testplane_nonlinear", "testplane_rot_sideslip_flaps", "testplane_swept_tapered", "testplane_airfoil_dist",
+         "testplane_constrained_sheet",
          "traditional_linear", "traditional_nonlinear", "flyingwing_nonlinear", "swarm_nonlinear"]
 
 

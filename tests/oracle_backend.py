@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE: stand-ins for machupx_b200.device.DeviceScene / BatchDeviceScene that answer with the CPU oracle
+(oracle/lls_oracle.py), so the HOST logic of machupx_b200.Scene -- table revisions, per-case tables of the batched
+finite-difference stencils, driver arithmetic, error policy -- can be exercised in the CPU test-suite against the reference's
+golden answers.  Nothing outside tests/ may import this module; the product has no CPU path (tests/test_abi.py checks)."""
+import numpy as np
+
+from machupx_b200 import layout as L
+from oracle import lls_oracle as O
+
+
+def _solve(tables, ac_state, solver_type, convergence, relaxation, max_iterations):
+    T = O.Tables(tables, ac_state)
+    res = O.solve(T, solver_type=solver_type, convergence=convergence, relaxation=relaxation, max_iterations=max_iterations)
+    status = 0 if res["converged"] else L.STATUS_NOT_CONVERGED
+    return res, status
+
+
+class OracleDeviceScene:
+    def __init__(self, tables, device=None):
+        self.tables = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in tables.items()}
+        self.n, self.ld = int(tables["n"]), int(tables["ld"])
+        self.n_aircraft, self.n_segments, self.flags = int(tables["n_aircraft"]), int(tables["n_segments"]), int(tables["flags"])
+        self.n_airfoils = len(tables["airfoils"])
+        self.bytes_h2d = self.bytes_d2h = 0
+        self.last_status = 0
+        self.uploads = ["tables"]
+        self._solver = ("linear",)
+
+    def upload_tables(self, tables):
+        self.tables.update(tab=np.array(tables["tab"], copy=True), itab=np.array(tables["itab"], copy=True),
+                           airfoils=np.array(tables["airfoils"], copy=True))
+        self.uploads.append("tables")
+
+    def upload_rows(self, tab, fields):
+        for f in fields:
+            self.tables["tab"][f] = tab[f]
+        self.uploads.append(("rows", tuple(fields)))
+
+    def upload_state(self, ac_state):
+        self.ac = np.array(L.pad_ac_state(ac_state), copy=True)
+
+    def flow_state(self):
+        self._solver = ("none",)
+
+    def build_influence(self, impingement_threshold=1e-10):
+        pass
+
+    def solve_linear(self):
+        self._solver = ("linear",)
+
+    def solve_nonlinear(self, convergence, relaxation, max_iterations):
+        self._solver = ("nonlinear", convergence, relaxation, max_iterations)
+        self._res, status = _solve(self.tables, self.ac, "nonlinear", convergence, relaxation, max_iterations)
+        return self._res["iterations"], self._res["error"], status, list(self._res["history"])
+
+    def integrate(self):
+        if self._solver[0] != "nonlinear":
+            self._res, _ = _solve(self.tables, self.ac, "linear", 1e-10, 1.0, 1)
+        return np.array(self._res["seg_fm"], copy=True)
+
+    def status(self):
+        return 0
+
+    def out(self):
+        out = np.zeros((L.NO, self.n))
+        out[L.O_GAMMA] = self._res["gamma"]
+        return out
+
+
+class OracleBatchDeviceScene:
+    def __init__(self, tables, ncases, device=None):
+        self.base = OracleDeviceScene(tables)
+        self.ncases = int(ncases)
+        self.n, self.ld, self.flags = self.base.n, self.base.ld, self.base.flags
+        self.n_aircraft, self.n_segments = self.base.n_aircraft, self.base.n_segments
+        self.case_tables = None
+        self.log = []
+
+    def upload_tables(self, tables):
+        self.base.upload_tables(tables)
+
+    def upload_rows(self, tab, fields):
+        self.base.upload_rows(tab, fields)
+
+    def upload_case_tables(self, case_tables):
+        assert np.shape(case_tables) == (self.ncases, L.NF, self.ld)
+        self.case_tables = np.array(case_tables, copy=True)
+        self.log.append("case_tables")
+
+    def use_shared_tables(self):
+        self.case_tables = None
+        self.log.append("shared")
+
+    def upload_states(self, ac_states):
+        self.ac = np.array(L.pad_ac_state(np.asarray(ac_states).reshape(self.ncases, self.n_aircraft, -1)), copy=True)
+
+    def solve(self, solver_type, convergence, relaxation, max_iterations, impingement_threshold=1e-10, linear_start=True):
+        nc = self.ncases
+        seg = np.zeros((nc, self.n_segments, 12))
+        its, err, status = np.zeros(nc, dtype=np.int32), np.zeros(nc), np.zeros(nc, dtype=np.int32)
+        for c in range(nc):
+            tables = dict(self.base.tables)
+            if self.case_tables is not None:
+                tables["tab"] = self.case_tables[c]
+            res, status[c] = _solve(tables, self.ac[c], solver_type, convergence, relaxation, max_iterations)
+            seg[c], its[c], err[c] = res["seg_fm"], res["iterations"], res["error"]
+        return seg, its, err, status
+
+
+def install(monkeypatch):
+    """Routes machupx_b200.Scene to the oracle stand-ins for the duration of one test."""
+    import machupx_b200.device as device
+    monkeypatch.setattr(device, "DeviceScene", OracleDeviceScene)
+    monkeypatch.setattr(device, "BatchDeviceScene", OracleBatchDeviceScene)

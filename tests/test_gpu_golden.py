@@ -219,6 +219,7 @@ def test_lu_switchable_variants(env):
 def test_lu_pivot_guard_flags_matrices_the_unpivoted_factorisation_cannot_trust():
     """the LU is unpivoted; a pivot six orders of magnitude below the largest raises LLS_STATUS_SMALL_PIVOT,
     a zero pivot LLS_STATUS_NAN (LAPACK: singular), and a dominant matrix raises neither."""
+    from machupx_b200 import layout as L
     from machupx_b200.device import DeviceScene
     n = 200
     ld = L.padded_ld(n)

@@ -190,8 +190,8 @@ def test_empty_scene_and_bad_requests_fail_like_the_reference():
     scene = _scene()
     with pytest.raises(ValueError):                            # a batch keeps the geometry: the position may not move
         scene._batch_rows("test_plane", [{"position": [0.0, 0.0, -10.0], "velocity": 100.0}])
-    with pytest.raises(NotImplementedError):                   # batched stencils report body and wind frames only
-        scene._batched_ok({"batched": True, "stab_frame": True})
+    # batched stencils build their totals with the same assembly as solve_forces: every frame is available
+    assert scene._batched_ok({"batched": True, "stab_frame": True}) is True
     assert scene._batched_ok({}) is False and scene._batched_ok({"batched": True}) is True
 
 

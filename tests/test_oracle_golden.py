@@ -87,3 +87,33 @@ def test_circulation_golden_file_of_the_reference():
     assert np.abs(res["gamma"] - g["circ_file"]).max() < 1e-11 * np.abs(g["circ_file"]).max()   # 12 printed digits
     assert np.abs(np.degrees(res["dist"]["alpha"]) - g["alpha_file"]).max() < 1e-10 or \
         np.abs(res["dist"]["alpha"] - g["alpha_file"]).max() < 1e-11
+
+
+def test_c3_sub_grid_cases_of_the_reference():
+    """The oracle on three corners of the reference's C3 sub-grid (tests/golden/api_scenarios.json "c3"): CL / CD / Cm and the
+    Newton iteration count of the reference's serial sweep loop."""
+    import copy
+    import json
+    import os
+    import api_scenarios as S
+    from machupx_b200 import Scene
+    from machupx_b200.forces import assemble_fm
+    from machupx_b200.tables import build_aircraft_state
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api_scenarios.json")) as fh:
+        gold = json.load(fh)["c3"]
+    inp = copy.deepcopy(gold["input"])
+    inp["solver"]["type"] = "nonlinear"
+    inp["solver"].pop("relaxation", None)
+    scene = Scene(inp)
+    name = gold["nonlinear"]["aircraft"]
+    states = S.c3_states(gold["alpha_idx"], gold["beta_idx"])
+    for case in (0, 27, 63):
+        scene.set_aircraft_state(states[case], aircraft=name)
+        scene._refresh_tables()
+        T = O.Tables(scene._tables, build_aircraft_state(scene))
+        res = O.solve(T, solver_type="nonlinear", convergence=scene._solver_convergence, relaxation=scene._solver_relaxation,
+                      max_iterations=scene._max_solver_iterations)
+        assert res["iterations"] == gold["nonlinear"]["iterations"][case]
+        tot = assemble_fm(res["seg_fm"], scene._frames())[name]["total"]
+        for key, val in gold["nonlinear"]["totals"][case].items():
+            assert abs(tot[key] - val) <= 1e-10 * max(1.0, abs(val)), (case, key)

@@ -56,20 +56,61 @@ def test_derivatives(which):
     _compare(res, GOLD["derivatives"][which], 2e-8 if which in ("damping", "all", "state") else 1e-9)
 
 
-@pytest.mark.parametrize("which", ["stability", "damping", "all"])
+@pytest.mark.parametrize("which", ["stability", "damping", "control", "all", "state"])
 def test_derivatives_batched(which):
-    """The same stencils as ONE batched device pass per aircraft (batched=True): against the reference's answers at the same
-    tolerances, and against the one-solve-at-a-time path."""
+    """The same stencils as ONE batched device pass per aircraft (batched=True; control and state stencils carry per-case
+    tables): against the reference's answers at the same tolerances."""
+    res = S.derivatives_case(_scene_cls(), BASE, which, batched=True)
+    _compare(res, GOLD["derivatives"][which], 2e-8 if which in ("damping", "all", "state") else 1e-9)
+
+
+@pytest.mark.parametrize("which", ["target_CL", "pitch_trim", "pitch_trim_finite_moment", "pitch_trim_orientation", "aero_center"])
+def test_other_methods_batched(which):
+    res = S.other_case(_scene_cls(), BASE, which, batched=True)
+    _compare(res, GOLD["other"][which], 1e-9)
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_export_pylot_model(tmp_path, batched):
+    """scene.py:3521-3747 (59 solves of the hot path): the file the reference writes, key by key."""
+    res = S.pylot_case(_scene_cls(), BASE, str(tmp_path / "pylot.json"), batched=batched)
+    ref = GOLD["pylot"]
+    assert set(res.keys()) == set(ref.keys())
+    for key, val in ref.items():
+        if key == "coefficients":
+            for k, v in val.items():
+                if isinstance(v, dict):
+                    for kk, vv in v.items():
+                        assert abs(res[key][k][kk] - vv) <= 2e-8 * max(1.0, abs(vv)), (k, kk)
+                elif isinstance(v, str):
+                    assert res[key][k] == v
+                else:
+                    assert abs(res[key][k] - v) <= 2e-8 * max(1.0, abs(v)), k
+        else:
+            assert res[key] == val, key
+
+
+@pytest.mark.parametrize("solver", ["linear", "nonlinear"])
+def test_c3_sweep_sub_grid_against_the_reference(solver):
+    """BASELINE.json configs[2]: the 8 x 8 sub-grid of the 64 x 64 alpha / beta sweep of examples/FlyingWing that
+    oracle/gen_api_golden.py ran through the reference's serial loop; here ONE batched device pass (Scene.solve_forces_batch).
+    All 24 totals to 1e-10 relative, Newton iteration counts equal."""
     import copy
-    scene = _scene_cls()(copy.deepcopy(BASE))
-    call = {"stability": scene.stability_derivatives, "damping": scene.damping_derivatives, "all": scene.derivatives}[which]
-    res = call(batched=True)
-    seq = call()
-    _compare(res, seq, 1e-9)
-    if which != "all":      # the golden "all" case also carries the stability frame, which a batch does not report
-        _compare(res, GOLD["derivatives"][which], 2e-8 if which == "damping" else 1e-9)
-    with pytest.raises(NotImplementedError):
-        scene.stability_derivatives(batched=True, stab_frame=True)
+    gold = GOLD["c3"]
+    inp = copy.deepcopy(gold["input"])
+    inp["solver"]["type"] = solver
+    inp["solver"].pop("relaxation", None)
+    scene = _scene_cls()(inp)
+    name = gold[solver]["aircraft"]
+    res = scene.solve_forces_batch(S.c3_states(gold["alpha_idx"], gold["beta_idx"]), aircraft=name)
+    assert res["converged"].all()
+    ref = gold[solver]["totals"]
+    for key in ref[0]:
+        r = np.array([t[key] for t in ref])
+        g = np.asarray(res["totals"][name][key])
+        assert np.abs(g - r).max() <= 1e-10 * max(1.0, np.abs(r).max()), key
+    if solver == "nonlinear":
+        assert [int(x) for x in res["iterations"]] == gold[solver]["iterations"]
 
 
 @pytest.mark.parametrize("which", ["target_CL", "pitch_trim", "pitch_trim_finite_moment", "pitch_trim_orientation", "aero_center", "MAC"])
