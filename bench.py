@@ -1,17 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the lifting-line solve path (BASELINE.json metric: lifting-line solves/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|testplane]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c2|swarm|testplane]
 
-One "step" = one steady-state ``solve_forces()`` on an already-built scene: flow state, V_ji influence
-build, linear solve, Newton iteration to 1e-10, force integration (reference: scene.py:1411-1532).
-Workload at N=1: BASELINE.json configs[1] — Traditional aeroplane refined to 4,000 control points,
-nonlinear solve.  At N>1 every rank solves the same scene at its own angle of attack (an alpha sweep
-sharded by case): weak scaling, no data-path collective.
+One "step" = one steady-state ``solve_forces()`` on an already-built scene: flow state, V_ji influence build, linear solve,
+Newton iteration to 1e-10, force integration (reference: scene.py:1411-1532).
 
-Prints ONE JSON line (rank 0).  `value` times the solve with the flight state already in HBM;
-`e2e` times the public host-side call including the pinned host->device copy of the flight state and
-the device->host read of the force sums, every step.
+Workloads
+  c2     BASELINE.json configs[1]: Traditional aeroplane refined to 4,000 control points, nonlinear.  The headline: one GPU
+         (a small single scene does not shard: SURVEY.md section 8e "replicas only").
+  swarm  the north-star's multi-GPU workload: ONE large multi-aircraft scene (the 32-aircraft lattice of SURVEY.md section 8d at
+         1,000 control points per aircraft = 32,000 control points; the reference cannot hold it: ~0.66 kB per pair = 680 GB),
+         rows of V_ji / J partitioned over the GPUs, distributed LU with the panels exchanged inside the kernels over NVLink
+         (DESIGN.md section 6.2).  STRONG scaling: the same scene at every N; on one GPU the fused single-GPU path solves it.
+  auto   (default) c2 when this process sees ONE GPU and N = 1; swarm when N > 1, and also at N = 1 when the box shows
+         several GPUs -- that run is the base point of a 1 -> 8 scaling series, and a series needs one workload throughout.
+         ``--workload`` overrides; ``--swarm-aircraft / --swarm-grid`` resize the swarm.
+
+Prints ONE JSON line (rank 0).  c2: ``value`` times the solve with the flight state already in HBM, ``e2e`` the public
+``Scene.solve_forces()`` call including the pinned host->device copy of the flight state and the device->host read of the
+residual norms and force sums, every step.  swarm: every step IS the public call (``Scene.solve_forces(partitioned=N > 1)``);
+``value`` is its device time (CUDA events around the steps on the launching stream, max over ranks) and ``e2e`` its wall clock.
+
+``--impl reference`` (c2): times the UNMODIFIED reference staged in oracle/_ref (oracle/stage_ref.py; MachUpX is pure Python,
+staging is a byte-for-byte copy) on the host cores: scene construction once, then ONE full solve_forces() as shipped (1 BLAS
+thread, machupX/__init__.py:1-6) and ONE with every core; the line's value is the faster.  (swarm: the reference is out of
+memory by two orders of magnitude; the arm reports the oracle port's phases measured at N = 4,000 and scaled.)
 """
 import argparse
 import json
@@ -39,24 +53,39 @@ UNIT = "solves/s"
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
+def visible_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def pick_workload(args):
+    if args.workload != "auto":
+        return args.workload
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1 or visible_gpus() >= 2:
+        return "swarm"
+    return "c2"
+
+
 def load_workload(name):
     """Returns (tables, ac_state, golden dict, meta).  Tables come from the committed fixtures generated
     from the reference's own JSON inputs (oracle/gen_golden.py); data are synthetic in the sense of
     BASELINE.json: a refined example scene, no measured flight data."""
     from golden_utils import load
-    fixture = {"c2": "c2_traditional_n4000", "testplane": "testplane_nonlinear", "swarm": "swarm_nonlinear"}[name]
+    fixture = {"c2": "c2_traditional_n4000", "testplane": "testplane_nonlinear", "swarm800": "swarm_nonlinear"}[name]
     return load(fixture)
 
 
-def with_alpha(ac_state, alpha_deg, meta):
-    """Flight state of rank r: same speed, angle of attack alpha_deg (airplane.py:300-316 convention)."""
-    from machupx_b200 import layout as L
-    st = np.array(ac_state, dtype=float)
-    v = -st[0, L.AC_VTRANS:L.AC_VTRANS + 3]
-    V = np.linalg.norm(v)
-    a = np.radians(alpha_deg)
-    st[0, L.AC_VTRANS:L.AC_VTRANS + 3] = -np.array([V * np.cos(a), 0.0, V * np.sin(a)])
-    return st
+def swarm_config(args, n, ld, solver):
+    return {"workload": "synthetic %d-aircraft swarm (examples/Swarm drone on the 8-column lattice of SURVEY.md section 8d, grid.N=%d per "
+                        "wing segment), ONE scene of %d control points, nonlinear Newton solve; rows of V_ji / J partitioned over "
+                        "the GPUs, distributed LU (BASELINE.json configs[3]-[4] family; strong scaling)" % (args.swarm_aircraft, args.swarm_grid, n),
+            "control_points": int(n), "aircraft": int(args.swarm_aircraft), "solver": solver,
+            "l2_policy": "working set (V_ji %.1f GB + J %.1f GB over all ranks) exceeds the 126 MB L2; no explicit flush" % (
+                n * 3.0 * ld * 8 / 1e9, float(ld) * ld * 8 / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -153,26 +182,100 @@ def cpu_sample(tables, ac_state, meta, threads):
     return 1.0 / total, total, parts
 
 
+def reference_solve(workload_input, all_cores=True, solves=1, timeout=3000):
+    """Runs oracle/ref_runner.py (the UNMODIFIED reference staged in oracle/_ref + the stand-ins of oracle/ref_stubs) in its own
+    process on ``workload_input`` and returns its JSON, or {"unavailable": why}."""
+    import tempfile
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "machupX", "scene.py")):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import stage_ref
+            stage_ref.stage()
+        except Exception:
+            pass
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "machupX", "scene.py")):
+        return {"unavailable": "oracle/_ref is not staged (run oracle/stage_ref.py where /root/reference exists)"}
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+        json.dump(workload_input, fh)
+        path = fh.name
+    try:
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), path, "--solves", str(solves)] + (["--all-cores-too"] if all_cores else [])
+        env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS")}
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        if out.returncode != 0 or not lines:
+            return {"unavailable": "ref_runner failed: " + (out.stderr.strip().splitlines() or ["?"])[-1][:200]}
+        return json.loads(lines[-1])
+    finally:
+        os.unlink(path)
+
+
+def swarm_port_estimate(n, iters, threads):
+    """CPU figure for a scene the reference cannot hold: the oracle port's phases measured on the N = 4,000 fixture and scaled
+    (pair work with N^2, LAPACK's dense solve with N^3)."""
+    tables, ac_state, g, meta = load_workload("c2")
+    v, total, parts = cpu_sample(tables, ac_state, meta, threads)
+    r2, r3 = (n / 4000.0) ** 2, (n / 4000.0) ** 3
+    pair = parts["build_s"] + parts["linear_assembly_s"] + 3 * parts["residual_s"] + iters * (parts["residual_s"] + parts["jacobian_s"])
+    est = pair * r2 + (iters + 1) * parts["dense_solve_s"] * r3
+    return est, parts
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    tables, ac_state, g, meta = load_workload(args.workload)
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):
-        v, total, parts = cpu_sample(tables, ac_state, meta, threads)
-        vals.append(v)
-    value = float(np.median(vals))
-    sample = ("oracle port (numpy/LAPACK restatement of scene.py:557-1117), %d BLAS threads: V_ji rows for 256 of N control points "
-              "scaled to N, + 1 linear assembly/solve, 1 residual, 1 Jacobian, 1 dense solve, combined as "
-              "1 build + 1 linear + iters x (residual+Jacobian+solve) + 3 residuals" % threads)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, tables, meta),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "parts": parts},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    workload = pick_workload(args)
+    t_start = time.perf_counter()
+    if workload == "swarm":
+        n = args.swarm_aircraft * 5 * args.swarm_grid
+        iters = 13
+        est, parts = swarm_port_estimate(n, iters, threads)
+        value = 1.0 / est
+        solver = {"type": "nonlinear", "convergence": 1e-10, "relaxation": 1.0, "max_iterations": 100}
+        sample = ("the unmodified reference cannot hold this scene (about 0.66 kB of RSS per control-point pair = %.0f GB, BASELINE.md "
+                  "section 2); oracle port (numpy/LAPACK restatement of scene.py:557-1117) timed on the N = 4,000 fixture with %d BLAS threads "
+                  "(V_ji rows for 256 control points scaled to N, one linear assembly / residual / Jacobian / dense solve) and scaled "
+                  "to N = %d: pair phases x (N/4000)^2, dense solves x (N/4000)^3, %d Newton iterations" % (0.66e3 * n * n / 1e9, threads, n, iters))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+                "steps_requested": args.steps, "warmup": 0, "ms_per_step": 1e3 * (time.perf_counter() - t_start), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": swarm_config(args, n, n, solver),
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                 "seconds_per_solve_extrapolated": est, "parts_at_n4000": parts, "reference": "out of memory"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "ms_per_step is the wall time of the sample this run measured, not the extrapolated solve (value = 1 / extrapolated seconds)"}
+        print(json.dumps(line))
+        return
+    tables, ac_state, g, meta = load_workload(workload)
+    ref = reference_solve(meta["input"], all_cores=True, solves=1)
+    port_v, port_total, port_parts = cpu_sample(tables, ac_state, meta, threads)
+    port = {"value": port_v, "unit": UNIT, "cores": threads, "kind": "port", "seconds_per_solve_extrapolated": port_total, "parts": port_parts,
+            "sample": "oracle port: V_ji rows for 256 of N control points scaled to N + 1 linear assembly/solve + 1 residual + 1 Jacobian + 1 "
+                      "dense solve, combined with the reference's Newton iteration count"}
+    if "unavailable" in ref:
+        value, kind, cores = port_v, "port", threads
+        sample = port["sample"] + " (" + ref["unavailable"] + ")"
+        settings = None
+    else:
+        a, b = ref["as_shipped_1_blas_thread"], ref.get("all_cores")
+        best = min([x["seconds_per_solve"] for x in (a, b) if x])
+        value, kind, cores = 1.0 / best, "reference", int(ref["cores"])
+        sample = ("UNMODIFIED reference (machupX %s staged in oracle/_ref, stand-ins for airfoil_db/matplotlib/numpy-stl) on %s: scene construction "
+                  "once (%.1f s, not counted), then ONE full Scene.solve_forces() as shipped (1 BLAS thread: %.1f s) and ONE with %d BLAS threads "
+                  "(%s); value = the faster" % ("2.7.2", workload_config(workload, tables, meta)["workload"].split(",")[0], ref["construct_s"],
+                                                 a["seconds_per_solve"], cores, ("%.1f s" % b["seconds_per_solve"]) if b else "not run"))
+        settings = {"as_shipped_1_blas_thread": a, "all_cores": b, "construct_s": ref["construct_s"],
+                    "parity_with_fixture": {"CL": a["CL"], "CL_fixture": meta["FM"][list(meta["FM"])[0]]["total"]["CL"]}}
+    wall = time.perf_counter() - t_start
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "steps_requested": args.steps,
+            "warmup": 0, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(workload, tables, meta),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "thread_settings": settings,
+                             "port_sample": port},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
     print(json.dumps(line))
 
 
@@ -180,7 +283,7 @@ def workload_config(name, tables, meta):
     desc = {"c2": "Traditional airplane refined to 4,000 control points (grid.N=800 per segment), nonlinear Newton solve, "
                   "relaxation 0.9, convergence 1e-10 (BASELINE.json configs[1])",
             "testplane": "reference unit-test aeroplane, 200 control points, nonlinear",
-            "swarm": "examples/Swarm, 4 aircraft, 800 control points, nonlinear"}[name]
+            "swarm800": "examples/Swarm, 4 aircraft, 800 control points, nonlinear"}[name]
     return {"workload": desc, "control_points": int(tables["n"]), "solver": meta["solver"],
             "l2_policy": "working set (V_ji %.0f MB + J %.0f MB) exceeds the 126 MB L2; no explicit flush" % (
                 tables["n"] * 3 * tables["ld"] * 8 / 1e6, tables["ld"] ** 2 * 8 / 1e6)}
@@ -189,7 +292,157 @@ def workload_config(name, tables, meta):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def run_ours_swarm(args):
+    """ONE large scene, rows partitioned over the ranks (strong scaling).  Every step is the public call."""
+    import copy
+    import ctypes
+    import warnings
+    import torch
+    import torch.distributed as dist
+    from machupx_b200 import Scene, _native
+    from workloads import swarm_input
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t0 = time.perf_counter()
+    scene = Scene(swarm_input(args.swarm_aircraft, args.swarm_grid))
+    host_setup_s = time.perf_counter() - t0
+    n = scene._N
+    partitioned = world > 1 or args.force_partitioned
+    lib = _native.load()
+
+    def step():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return scene.solve_forces(partitioned=True) if partitioned else scene.solve_forces()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t0 = time.perf_counter()
+    FM = step()
+    barrier()
+    first_solve_s = time.perf_counter() - t0
+    for _ in range(max(3, args.warmup) - 1):
+        FM = step()
+    dev = scene._part_device if partitioned else scene._device
+    if partitioned and dev.fused_exchange:
+        dev.exchange_stats()          # reset the wait timers
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = lib.lls_launch_count()
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        FM = step()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    dev_ms = e0.elapsed_time(e1)
+    launches = lib.lls_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    exch = dev.exchange_stats() if (partitioned and dev.fused_exchange) else None
+    iters = int(scene._last_iterations)
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = t.tolist()
+        its = torch.zeros(world, dtype=torch.int32, device="cuda")
+        its[rank] = iters
+        dist.all_reduce(its)
+        per_rank_iters = [int(x) for x in its.tolist()]
+        waits = torch.zeros(world, 2, dtype=torch.float64, device="cuda")
+        if exch is not None:
+            waits[rank, 0], waits[rank, 1] = exch["panel_wait_ms"] / args.steps, exch["slot_wait_ms"] / args.steps
+        dist.all_reduce(waits)
+        waits = waits.tolist()
+    else:
+        per_rank_iters = [iters]
+        waits = [[exch["panel_wait_ms"] / args.steps, exch["slot_wait_ms"] / args.steps]] if exch is not None else None
+
+    # per-phase device times: one instrumented solve outside the timed region (the phase timers synchronise)
+    _native.check(lib.lls_set_timing(dev.handle, 1))
+    step()
+    ms = (ctypes.c_double * 6)()
+    _native.check(lib.lls_get_timings(dev.handle, ms))
+    _native.check(lib.lls_set_timing(dev.handle, 0))
+    tm = dict(zip(("influence", "assemble", "lu", "trisolve", "residual", "integrate"), list(ms)))
+    if world > 1:
+        t = torch.tensor([tm[k] for k in sorted(tm)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tm = dict(zip(sorted(tm), t.tolist()))
+    barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = ctypes_double4()
+    _native.check(lib.lls_probe_peaks(peaks, None))
+    fp64_dfma, fp64_dmma, copy_gbs = peaks[0], peaks[1], peaks[3]
+    n_fact = iters + 1
+    lu_flops = n_fact * (2.0 / 3.0) * float(n) ** 3
+    lu_tflops_per_gpu = lu_flops / (tm["lu"] * 1e-3) * 1e-12 / world if tm["lu"] > 0 else 0.0
+    names = list(FM.keys())
+    solver = {"type": scene._solver_type, "convergence": scene._solver_convergence, "relaxation": scene._solver_relaxation,
+              "max_iterations": scene._max_solver_iterations}
+    value = args.steps / (dev_ms * 1e-3)
+    e2e_value = args.steps / (wall_ms * 1e-3)
+    h2d = scene._num_aircraft * 16 * 8
+    d2h = scene._tables["n_segments"] * 12 * 8 + 8 * (iters + 1) + 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": swarm_config(args, n, dev.ld, solver),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": wall_ms / args.steps,
+                "note": "value and e2e come from the same steps, each one public Scene.solve_forces() call: value = CUDA-event time on the "
+                        "launching stream, e2e = wall clock (host->device copy of the flight state, device->host reads of residual norms, "
+                        "status and segment force sums inside)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"kernel": ("lu_dist_update_kernel (DMMA trailing update of the local rows) + owner/panel kernels of the row-partitioned LU"
+                                if partitioned else "lu_step_kernel: blocked FP64 LU, rank-128 paired block steps (DMMA mma.sync m8n8k4)"),
+                     "bound": "tensor", "achieved": lu_tflops_per_gpu, "peak": fp64_dmma, "unit": "TFLOP/s",
+                     "frac": lu_tflops_per_gpu / fp64_dmma if fp64_dmma else None, "traffic": None,
+                     "peak_source": "FP64 DMMA probe run live by this process (MEASURED_PEAKS.json has no FP64 entry); achieved is PER GPU: "
+                                    "(Newton iterations + 1) x 2/3 N^3 flop / LU phase time / n_gpus",
+                     "flops_per_solve": lu_flops, "ms_per_solve": tm["lu"], "factorisations_per_solve": n_fact},
+        "phase_ms": tm,
+        "exchange": {"path": ("peer-memory mailboxes (owner kernel stores panels into every GPU over NVLink, flags, one-panel look-ahead)"
+                              if (partitioned and dev.fused_exchange) else ("NCCL broadcast per block step" if partitioned else "none (one GPU)")),
+                     "per_rank_wait_ms_per_step": {"panel_wait, slot_wait": waits},
+                     "note": "panel_wait = time block 0 of the L-panel kernels spent waiting for the owner's panel to land (exposed "
+                             "exchange + owner-panel latency); slot_wait = time owner kernels waited for a free mailbox slot"},
+        "per_rank_newton_iterations": per_rank_iters,
+        "parity": {"newton_iterations": iters, "final_residual": float(scene._last_error),
+                   "CL_sum": float(sum(FM[k]["total"]["CL"] for k in names)), "CD_sum": float(sum(FM[k]["total"]["CD"] for k in names)),
+                   "CL_first": float(FM[names[0]]["total"]["CL"]),
+                   "note": "the reference cannot run this scene; compare CL_sum / iterations across the n_gpus of a scaling series, and "
+                           "tests/test_partitioned_gpu.py for oracle row checks"},
+        "host_setup_s": host_setup_s, "first_solve_s": first_solve_s,
+        "peaks": {"fp64_dfma_tflops": fp64_dfma, "fp64_dmma_tflops": fp64_dmma, "copy_gbs_live": copy_gbs},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
+    if pick_workload(args) == "swarm":
+        return run_ours_swarm(args)
+    args.workload = pick_workload(args)
     import torch
     import torch.distributed as dist
     from machupx_b200 import _native
@@ -214,9 +467,8 @@ def run_ours(args):
     nonlinear = sp["type"] == "nonlinear"
     # the public API object: JSON input of the fixture -> Scene (host geometry, O(N) tables) -> DeviceScene
     scene = Scene(copy.deepcopy(meta["input"]))
-    if world > 1:   # alpha sweep sharded by case: rank r flies at alpha0 + 0.25 deg * r (first aircraft)
-        name = list(scene._airplanes.keys())[0]
-        scene._airplanes[name].set_aerodynamic_state(alpha=2.0 + 0.25 * rank)
+    # world > 1 with this workload: independent replicas of the same solve, equal work on every rank (a small single scene does
+    # not shard: SURVEY.md section 8e)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         scene.solve_forces()
@@ -391,7 +643,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "testplane", "swarm"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "testplane", "swarm800", "swarm"])
+    ap.add_argument("--swarm-aircraft", type=int, default=32)
+    ap.add_argument("--swarm-grid", type=int, default=200)
+    ap.add_argument("--force-partitioned", action="store_true", help="swarm on one GPU through the partitioned kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

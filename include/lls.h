@@ -40,7 +40,8 @@ extern "C" {
 #define LLS_STATUS_IMPINGEMENT 2
 #define LLS_STATUS_NAN 4
 #define LLS_STATUS_SMALL_PIVOT 8
-#define LLS_STATUS_BITS 5 /* number of status bits defined below */
+#define LLS_STATUS_BITS 6 /* number of status bits defined below */
+#define LLS_STATUS_COMM 32 /* row-partitioned solve: a rank waited 30 s for a peer's data (a peer died or fell out of step) */
 #define LLS_STATUS_SECTION_BOUNDS 16 /* a poly_fit airfoil was evaluated outside the limits of its fit (airfoil_db: PolyFitBoundsError) */
 
 /* ---- solver flags (reference: scene.py:82-87) ------------------------------------------ */
@@ -231,6 +232,27 @@ int lls_dist_lu_step_doubles(lls_scene* h, int k, size_t* doubles);
 int lls_dist_lu_owner(lls_scene* h, int k, int with_rhs, double* d_step, void* stream);
 int lls_dist_lu_update(lls_scene* h, int k, int with_rhs, const double* d_step, void* stream);
 int lls_dist_back(lls_scene* h, int k, void* stream);
+
+/* The same factorisation with the exchange inside the kernels, over NVLink peer memory (no collective call and no host code
+ * between two block steps).  Every rank owns a "mailbox" (panel slots, arrival flags, progress counters,
+ * the replicated solution) in device memory that the LIBRARY allocates (cudaMalloc: the one large buffer it owns, because only a
+ * whole cudaMalloc allocation can be exported through CUDA IPC) and that every other rank maps into its process:
+ *   lls_dist_comm_create  : after lls_bind; allocates the mailbox (`slots` panel slots, 2..32) and returns its 64-byte
+ *                           cudaIpcMemHandle_t (zeros when world == 1)
+ *   lls_dist_comm_connect : all_handles = world x 64 bytes in rank order (the host gathers them, e.g. torch.distributed
+ *                           all_gather); opens the peers' mailboxes.  A no-op when world == 1.
+ *   lls_dist_lu_solve     : factorises the matrix the ranks hold with the right-hand side carried along and back-substitutes:
+ *                           x (lls_dist_vectors) is replicated on return.  Owner kernels store their panel straight into every
+ *                           rank's slot and release an arrival flag; the next panel is pushed one step ahead (look-ahead).
+ *                           A peer that never arrives raises LLS_STATUS_COMM after 30 s instead of hanging.
+ *   lls_dist_comm_stats   : out4 = {ms the panel kernels waited for panels, ms the owner kernels waited for free slots,
+ *                           global block steps so far, back substitutions so far}; resets the two timers.
+ *   lls_dist_comm_destroy : closes the peers' mailboxes and frees the own one (also done by lls_destroy). */
+int lls_dist_comm_create(lls_scene* h, int slots, unsigned char* ipc_handle_out64);
+int lls_dist_comm_connect(lls_scene* h, const unsigned char* all_handles);
+int lls_dist_lu_solve(lls_scene* h, void* stream);
+int lls_dist_comm_stats(lls_scene* h, double* out4, void* stream);
+int lls_dist_comm_destroy(lls_scene* h);
 
 /* Per-aircraft flight state, n_aircraft * LLS_AC_STRIDE doubles on the device
  * (reference: Airplane.set_state airplane.py:105-213 -> scene.py:562-582). */

@@ -44,6 +44,11 @@ SIGNATURES = {
     "lls_dist_lu_owner": (_i, [_vp, _i, _i, _vp, _vp]),
     "lls_dist_lu_update": (_i, [_vp, _i, _i, _vp, _vp]),
     "lls_dist_back": (_i, [_vp, _i, _vp]),
+    "lls_dist_comm_create": (_i, [_vp, _i, _vp]),
+    "lls_dist_comm_connect": (_i, [_vp, _vp]),
+    "lls_dist_lu_solve": (_i, [_vp, _vp]),
+    "lls_dist_comm_stats": (_i, [_vp, _pd, _vp]),
+    "lls_dist_comm_destroy": (_i, [_vp]),
     "lls_set_state": (_i, [_vp, _vp]),
     "lls_flow_state": (_i, [_vp, _vp]),
     "lls_build_influence": (_i, [_vp, _d, _vp]),

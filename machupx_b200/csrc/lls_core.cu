@@ -123,6 +123,7 @@ extern "C" int lls_create(lls_scene** out, int n, int n_aircraft, int n_segments
 
 extern "C" int lls_destroy(lls_scene* h) {
     if (h == nullptr) return LLS_OK;
+    dist_comm_destroy(h);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->ev[0]) cudaEventDestroy(h->ev[0]);
@@ -421,6 +422,35 @@ extern "C" int lls_dist_back(lls_scene* h, int k, void* stream) {
     LLS_REQUIRE(k >= 0 && k < h->ld / LU_NB, LLS_ERR_ARG, "lls_dist_back: bad arguments");
     PhaseTimer t(h, (cudaStream_t)stream, 3);
     return lu_dist_back(h, k, wf(h, W_RHS), wf(h, W_X), (cudaStream_t)stream);
+}
+
+extern "C" int lls_dist_comm_create(lls_scene* h, int slots, unsigned char* ipc_handle_out64) {
+    LLS_CHECK_BOUND(h);
+    LLS_CHECK_PART(h);
+    return dist_comm_create(h, slots, ipc_handle_out64);
+}
+
+extern "C" int lls_dist_comm_connect(lls_scene* h, const unsigned char* all_handles) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(all_handles != nullptr || h->cs.P == 1, LLS_ERR_ARG, "lls_dist_comm_connect: null handles");
+    return dist_comm_connect(h, all_handles);
+}
+
+extern "C" int lls_dist_lu_solve(lls_scene* h, void* stream) {
+    LLS_CHECK_BOUND(h);
+    LLS_CHECK_PART(h);
+    PhaseTimer t(h, (cudaStream_t)stream, 2);
+    return lu_dist_factor_solve_p2p(h, wf(h, W_RHS), wf(h, W_X), (cudaStream_t)stream);
+}
+
+extern "C" int lls_dist_comm_stats(lls_scene* h, double* out4, void* stream) {
+    LLS_REQUIRE(h != nullptr && out4 != nullptr, LLS_ERR_ARG, "lls_dist_comm_stats: null argument");
+    return dist_comm_stats(h, out4, (cudaStream_t)stream);
+}
+
+extern "C" int lls_dist_comm_destroy(lls_scene* h) {
+    LLS_REQUIRE(h != nullptr, LLS_ERR_ARG, "lls_dist_comm_destroy: null handle");
+    return dist_comm_destroy(h);
 }
 
 extern "C" int lls_get_status(lls_scene* h, void* stream, int* status) {

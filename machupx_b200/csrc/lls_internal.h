@@ -112,6 +112,7 @@ struct Scene {
     bool timing = false;
     double ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    void* dist = nullptr;       // DistComm of the row-partitioned LU over peer memory (lu_dist.cu), created by lls_dist_comm_create
 };
 
 inline CaseStrides strides(const Scene* s, bool masked) {
@@ -142,6 +143,12 @@ int lu_dist_begin(Scene* s, cudaStream_t st);
 int lu_dist_owner(Scene* s, int k, double* rhs, double* send, cudaStream_t st);
 int lu_dist_update(Scene* s, int k, double* rhs, const double* recv, cudaStream_t st);
 int lu_dist_back(Scene* s, int k, const double* y, double* x, cudaStream_t st);
+// row-partitioned LU with the exchange inside the kernels (mailboxes in peer memory, CUDA IPC between the processes)
+int dist_comm_create(Scene* s, int slots, unsigned char* handle64);
+int dist_comm_connect(Scene* s, const unsigned char* handles);
+int dist_comm_destroy(Scene* s);
+int dist_comm_stats(Scene* s, double* out4, cudaStream_t st);
+int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st);
 
 }  // namespace lls
 

@@ -38,8 +38,8 @@ FLAG_SWEPT_SECTIONS, FLAG_TOTAL_VELOCITY, FLAG_IN_PLANE, FLAG_MATCH_MACHUP_PRO, 
 FLAG_DEFAULT = FLAG_SWEPT_SECTIONS | FLAG_TOTAL_VELOCITY | FLAG_IN_PLANE
 
 # status bits
-STATUS_NOT_CONVERGED, STATUS_IMPINGEMENT, STATUS_NAN, STATUS_SMALL_PIVOT, STATUS_SECTION_BOUNDS = 1, 2, 4, 8, 16
-STATUS_BITS = 5
+STATUS_NOT_CONVERGED, STATUS_IMPINGEMENT, STATUS_NAN, STATUS_SMALL_PIVOT, STATUS_SECTION_BOUNDS, STATUS_COMM = 1, 2, 4, 8, 16, 32
+STATUS_BITS = 6
 
 LD_ALIGN = 64  # leading dimension is N rounded up to this many elements
 

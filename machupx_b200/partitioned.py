@@ -74,6 +74,11 @@ class PartitionedSolver:
     def lu_solve(self):
         """Factor the matrix the ranks hold, carry the right-hand side along, back-substitute: x replicated on return."""
         ops, comm = self.ops, self.comm
+        if getattr(ops, "fused_exchange", False):
+            # device path: the whole factorisation + back substitution is enqueued by ONE library call; the panels travel between
+            # the GPUs inside the kernels (peer-memory mailboxes), so there is nothing for the host to do per block step
+            ops.lu_solve_fused()
+            return
         ops.lu_begin()
         for k in range(self.nblk):
             owner = owner_of_block(k, self.world)
@@ -153,7 +158,9 @@ class TorchComm:
 class PartitionedDeviceScene:
     """Device side of a partitioned scene on this rank's GPU; also the ``ops`` object of ``PartitionedSolver``."""
 
-    def __init__(self, tables, group=None, device=None):
+    def __init__(self, tables, group=None, device=None, shard=None):
+        """``shard = (world, rank)`` builds ONE rank's share of a partition without a process group (no exchange possible: for
+        checking the row-local kernels -- influence build, assembly, residual -- of scenes that need several GPUs on a single one)."""
         import torch
         import torch.distributed as dist
         from . import _native
@@ -163,6 +170,8 @@ class PartitionedDeviceScene:
         self.lib = _native.load()
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if shard is not None:
+            self.world, self.rank = int(shard[0]), int(shard[1])
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.n = int(tables["n"])
         sizes = _native.Sizes()
@@ -199,7 +208,8 @@ class PartitionedDeviceScene:
             off = x.value - self.d_work.data_ptr()
             self.d_x = self.d_work[off:off + self.ld * 8].view(torch.float64)      # replicated Newton step / solution
         self.impingement_threshold = 1e-10
-        self.comm = TorchComm(group, dev) if dist.is_initialized() else LocalComm()
+        self.comm = TorchComm(group, dev) if dist.is_initialized() and shard is None else LocalComm()
+        self.fused_exchange = self._connect_mailboxes(group) if shard is None else False
         self.solver = PartitionedSolver(self, self.comm, self.nblk, self.world, self.rank)
         # One factorisation + back substitution = 3 launches and 1-2 broadcasts per block step, thousands of tiny host calls:
         # after a warm-up pass it is captured into a CUDA graph (NCCL broadcasts included) and replayed.
@@ -227,6 +237,49 @@ class PartitionedDeviceScene:
             self._lu_graph.replay()
 
         self.solver.lu_solve = lu_solve_graphed
+
+    def _connect_mailboxes(self, group):
+        """Peer-memory exchange of the LU (include/lls.h, lls_dist_comm_*): every rank allocates its mailbox, the 64-byte CUDA IPC
+        handles are gathered through torch.distributed, every rank maps the others' mailboxes.  Returns False -- on EVERY rank --
+        if any rank cannot (no peer access between the GPUs, IPC not permitted): the solve then uses the step-wise path with
+        NCCL broadcasts.  ``LLS_PARTITIONED_P2P=0`` forces that path."""
+        torch = self.torch
+        import torch.distributed as dist
+        if os.environ.get("LLS_PARTITIONED_P2P", "1") != "1":
+            return False
+        ok = 1
+        handle = (ctypes.c_ubyte * 64)()
+        try:
+            self._call(self.lib.lls_dist_comm_create, int(os.environ.get("LLS_PARTITIONED_SLOTS", "8")), handle)
+        except self._native.LlsError as exc:
+            ok, self.exchange_error = 0, repr(exc)
+        if self.world > 1:
+            mine = torch.tensor(list(bytes(handle)) + [ok], dtype=torch.uint8, device=self.device)
+            every = torch.empty(self.world * 65, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu().numpy().reshape(self.world, 65)
+            ok = int(every[:, 64].min())
+            if ok:
+                blob = (ctypes.c_ubyte * (64 * self.world)).from_buffer_copy(np.ascontiguousarray(every[:, :64]).tobytes())
+                try:
+                    self._call(self.lib.lls_dist_comm_connect, blob)
+                except self._native.LlsError as exc:
+                    ok, self.exchange_error = 0, repr(exc)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            ok = int(flag.item())
+        if not ok:
+            self._native.check(self.lib.lls_dist_comm_destroy(self.handle))
+        return bool(ok)
+
+    def lu_solve_fused(self):
+        self._call(self.lib.lls_dist_lu_solve, self._st())
+
+    def exchange_stats(self):
+        """{panel_wait_ms, slot_wait_ms, block_steps, back_substitutions} since the last call (fused exchange only)."""
+        out = (ctypes.c_double * 4)()
+        self._call(self.lib.lls_dist_comm_stats, out, self._st())
+        return {"panel_wait_ms": out[0], "slot_wait_ms": out[1], "block_steps": int(out[2]), "back_substitutions": int(out[3])}
 
     def __del__(self):
         try:
@@ -309,6 +362,9 @@ class PartitionedDeviceScene:
         if failed:
             status |= L.STATUS_NOT_CONVERGED
         torch.cuda.synchronize(self.device)
+        if status & L.STATUS_COMM:
+            raise self._native.LlsError("row-partitioned solve: a rank waited 30 s for a peer's panel (LLS_STATUS_COMM); "
+                                        "a peer process died or the ranks fell out of step")
         return seg.reshape(self.n_segments, 12), it, err, status, hist
 
     def gamma(self):

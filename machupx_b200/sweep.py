@@ -48,9 +48,32 @@ class SceneCaseSolver:
         return np.array([tot.get(k, np.nan) for k in TOTAL_KEYS]), self.scene._last_iterations
 
 
+class BatchSceneSolver:
+    """Block solver: the rank's whole shard of cases goes through ``Scene.solve_forces_batch`` -- one batched device pass
+    (case index in blockIdx.z of every kernel) per ``max_batch`` cases instead of one solve per case.  This is the path
+    BASELINE.json configs[2] is measured on."""
+
+    def __init__(self, scene_input, aircraft=None, max_batch=4096):
+        from .scene import Scene
+        self.scene = Scene(scene_input)
+        self.scene.set_err_state(not_converged="ignore")       # non-convergence is reported per case, raised by run_sweep
+        self.aircraft = aircraft if aircraft is not None else list(self.scene._airplanes.keys())[0]
+        self.max_batch = int(max_batch)
+
+    def solve_block(self, first_case, states):
+        """-> (values (m, len(TOTAL_KEYS)), newton iterations (m,), converged (m,)) for the m states of this rank's shard."""
+        if len(states) == 0:
+            return np.zeros((0, len(TOTAL_KEYS))), np.zeros(0, dtype=int), np.zeros(0, dtype=bool)
+        res = self.scene.solve_forces_batch(states, aircraft=self.aircraft, max_batch=self.max_batch)
+        tot = res["totals"][self.aircraft]
+        values = np.stack([np.asarray(tot[k], dtype=float) for k in TOTAL_KEYS], axis=1)
+        return values, np.asarray(res["iterations"], dtype=int), np.asarray(res["converged"], dtype=bool)
+
+
 def run_sweep(states, solver, group=None, on_not_converged="raise"):
     """Solves ``states`` (list of state dicts) sharded over the ranks of ``group`` (``torch.distributed``; None = single
-    process).  ``solver(case_index, state)`` returns ``(values[len(TOTAL_KEYS)], newton_iterations)`` or None if the case
+    process).  A solver with a ``solve_block(first_case, states)`` method (``BatchSceneSolver``) gets its rank's whole shard at
+    once; otherwise ``solver(case_index, state)`` returns ``(values[len(TOTAL_KEYS)], newton_iterations)`` or None if the case
     did not converge.  Returns ``(table (n_cases, len(TOTAL_KEYS)), iterations (n_cases,), converged (n_cases,) bool)`` on
     every rank.  ``on_not_converged``: "raise" (the reference's default error policy; raised on every rank after the
     gather so no rank is left waiting in a collective) or "nan"."""
@@ -63,13 +86,19 @@ def run_sweep(states, solver, group=None, on_not_converged="raise"):
     lo, hi = shard_cases(n, world, rank)
     width = len(TOTAL_KEYS) + 2                       # values, iterations, converged flag
     local = np.full((hi - lo, width), np.nan)
-    for i in range(lo, hi):
-        res = solver(i, states[i])
-        if res is None:
-            local[i - lo, -2:] = (0.0, 0.0)
-        else:
-            local[i - lo, :len(TOTAL_KEYS)] = res[0]
-            local[i - lo, -2:] = (float(res[1]), 1.0)
+    if hasattr(solver, "solve_block"):                 # the rank's shard as batched device passes
+        values, its, ok = solver.solve_block(lo, states[lo:hi])
+        local[:, :len(TOTAL_KEYS)] = values
+        local[:, -2], local[:, -1] = its, ok
+        local[~np.asarray(ok, dtype=bool), :len(TOTAL_KEYS)] = np.nan
+    else:
+        for i in range(lo, hi):
+            res = solver(i, states[i])
+            if res is None:
+                local[i - lo, -2:] = (0.0, 0.0)
+            else:
+                local[i - lo, :len(TOTAL_KEYS)] = res[0]
+                local[i - lo, -2:] = (float(res[1]), 1.0)
     if distributed:
         backend = dist.get_backend(group)
         dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")

@@ -39,7 +39,8 @@ for name in names:
     if rank == 0:
         print(json.dumps({"fixture": name, "world": world, "n": int(tables["n"]), "ld": dev.ld, "gamma_rel_err": e_g, "force_rel_err": e_f,
                           "iterations": it, "reference_iterations": int(meta["iterations"]), "final_error": err, "status": status,
-                          "solve_s": t2 - t1, "first_solve_s": t1 - t0, "ok": bool(good)}), flush=True)
+                          "solve_s": t2 - t1, "first_solve_s": t1 - t0, "fused_exchange": bool(dev.fused_exchange),
+                          "exchange_stats": dev.exchange_stats() if dev.fused_exchange else None, "ok": bool(good)}), flush=True)
     del dev
 if world > 1:
     dist.destroy_process_group()

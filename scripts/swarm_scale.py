@@ -25,24 +25,8 @@ n_ac = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 grid_n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 check_rows = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 
-base = json.load(open(os.path.join(ROOT, "tests/golden/swarm_nonlinear.json")))["input"]
-inp = copy.deepcopy(base)
-drone = copy.deepcopy(next(iter(base["scene"]["aircraft"].values())))
-for w in drone["file"]["wings"].values():
-    w.setdefault("grid", {})["N"] = grid_n
-if n_ac == 4:
-    for ac in inp["scene"]["aircraft"].values():
-        ac["file"] = copy.deepcopy(drone["file"])
-else:
-    side = int(round(np.sqrt(n_ac)))
-    rng = np.random.default_rng(0)
-    inp["scene"]["aircraft"] = {}
-    for r in range(side):
-        for c in range(side):
-            ac = copy.deepcopy(drone)
-            eps = float(rng.uniform(-0.5, 0.5))
-            ac["state"]["position"] = [-10.0 * r, 10.0 * (c - (side - 1) / 2.0), -50.0 - 5.0 * ((r + c) % 2) + eps]
-            inp["scene"]["aircraft"]["drone_%d_%d" % (r, c)] = ac
+from workloads import swarm_input
+inp = swarm_input(n_ac, grid_n)
 t0 = time.perf_counter(); scene = Scene(inp); t_host = time.perf_counter() - t0
 dev = PartitionedDeviceScene(scene._tables)
 dev.upload_state(build_aircraft_state(scene))
@@ -68,7 +52,8 @@ out = {"world": world, "control_points": scene._N, "ld": dev.ld, "aircraft": sce
        "first_solve_s": t_first, "steady_solve_s": t_solve, "newton_iterations": it, "final_residual": err, "status": status,
        "CL_first_last": [FM[k]["total"]["CL"] for k in (list(FM)[0], list(FM)[-1])],
        "CL_sum": float(sum(v["total"]["CL"] for v in FM.values())), "CD_sum": float(sum(v["total"]["CD"] for v in FM.values())),
-       "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "phase_ms": tm}
+       "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "phase_ms": tm,
+       "fused_exchange": bool(dev.fused_exchange), "exchange_stats": dev.exchange_stats() if dev.fused_exchange else None}
 if check_rows > 0:
     from oracle import lls_oracle as O      # checker only
     T = O.Tables(scene._tables, build_aircraft_state(scene)); F = O.flow_state(T)

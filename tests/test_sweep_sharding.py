@@ -88,3 +88,61 @@ def test_gloo_sharded_sweep(world, n_alpha, n_beta, fail_case):
             good = np.arange(len(states)) != fail_case
             assert np.array_equal(table[good], exp[good]) and np.isnan(table[fail_case]).all()
             assert not ok[fail_case] and ok[good].all()
+
+
+# ---- the batched block path: every rank's shard as ONE Scene.solve_forces_batch pass ---------------------------------------------
+def _batch_worker(rank, world, port, q):
+    import json
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import api_scenarios as S
+        import machupx_b200.device as device
+        import oracle_backend
+        from machupx_b200.sweep import BatchSceneSolver
+        device.BatchDeviceScene = oracle_backend.OracleBatchDeviceScene      # CPU stand-in of the device (tests only)
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api_scenarios.json")) as fh:
+            gold = json.load(fh)["c3"]
+        inp = gold["input"]
+        inp["solver"]["type"] = "nonlinear"
+        inp["solver"].pop("relaxation", None)
+        solver = BatchSceneSolver(inp)
+        states = S.c3_states(S.C3_SUB[::2], S.C3_SUB[::2])
+        table, its, ok = run_sweep(states, solver)
+        q.put((rank, table, its, ok, solver.scene._batch_device.ncases))
+    except Exception as e:   # noqa: BLE001
+        q.put((rank, repr(e), None, None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_sharded_batched_sweep_against_the_reference_c3_golden():
+    """world_size 2 over gloo: rank r solves its contiguous half of a 4 x 4 sub-grid of BASELINE.json configs[2] as one batch
+    (device replaced by the oracle stand-in), one all_gather, and every rank holds the reference's totals and iteration
+    counts (tests/golden/api_scenarios.json "c3", generated by the reference's serial loop)."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import api_scenarios as S
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api_scenarios.json")) as fh:
+        gold = json.load(fh)["c3"]["nonlinear"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pick = [8 * a + b for a in range(0, 8, 2) for b in range(0, 8, 2)]          # positions of the 4 x 4 cases in the 8 x 8 golden
+    ref = np.array([[gold["totals"][i][k] for k in TOTAL_KEYS] for i in pick])
+    ref_its = np.array([gold["iterations"][i] for i in pick])
+    for rank, table, its, ok, ncases in results:
+        assert not isinstance(table, str), table
+        assert ncases == 8                                                      # the rank's whole shard in one batch
+        assert ok.all() and np.array_equal(its, ref_its)
+        assert np.abs(table - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
