@@ -264,7 +264,7 @@ def run_reference(args):
         value, kind, cores = 1.0 / best, "reference", int(ref["cores"])
         sample = ("UNMODIFIED reference (machupX %s staged in oracle/_ref, stand-ins for airfoil_db/matplotlib/numpy-stl) on %s: scene construction "
                   "once (%.1f s, not counted), then ONE full Scene.solve_forces() as shipped (1 BLAS thread: %.1f s) and ONE with %d BLAS threads "
-                  "(%s); value = the faster" % ("2.7.2", workload_config(workload, tables, meta)["workload"].split(",")[0], ref["construct_s"],
+                  "(%s); value = the faster" % ("2.7.2", "the %d-control-point scene" % int(ref["control_points"]), ref["construct_s"],
                                                  a["seconds_per_solve"], cores, ("%.1f s" % b["seconds_per_solve"]) if b else "not run"))
         settings = {"as_shipped_1_blas_thread": a, "all_cores": b, "construct_s": ref["construct_s"],
                     "parity_with_fixture": {"CL": a["CL"], "CL_fixture": meta["FM"][list(meta["FM"])[0]]["total"]["CL"]}}
