@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         LU_CLK(5);
         // everything below is off the critical path of the panel CTAs
         store_tile(gC, ld, sC);
-        pivot_guard<NT>(sC, pl, blk, ld / NB, scalars, status);
+        pivot_guard<NT>(sC, pl, blk == 0, blk == ld / NB - 1, scalars, status);
         if (rhs != nullptr && t < 32) forward_rhs_warp(sC, rhs + (size_t)blk * NB);
         // W = U11, pre-scaled rows in sA: the solve below turns the identity into inv(U11) (unless an INV CTA does that)
     } else {

@@ -24,7 +24,7 @@ constexpr int DIST_HDR = PUB_DOUBLES + NB;      // doubles before the packed U t
 __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_owner_kernel(double* __restrict__ Mloc, int ld, int k, int lbk, int ncols,
                                                                       double* __restrict__ rhs, double* __restrict__ send,
                                                                       double* __restrict__ uinv, int* __restrict__ flags, int epoch,
-                                                                      double* __restrict__ scalars, int* __restrict__ status) {
+                                                                      double* __restrict__ scalars, int* __restrict__ status, int last_owned) {
     extern __shared__ __align__(16) double sm[];
     double* sA = sm;
     double* sC = sm + NB * TS;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_owner_kernel(double* __
         __syncthreads();
         if (t == 0) st_release(flags + k, epoch);
         store_tile(gC, ld, sC);
-        pivot_guard<LU_THREADS>(sC, pl, k, ld / NB, scalars, status);
+        pivot_guard<LU_THREADS>(sC, pl, lbk == 0, last_owned != 0, scalars, status);
         if (rhs != nullptr && t < 32) {
             forward_rhs_warp(sC, rhs + (size_t)k * NB);
             __syncwarp();
@@ -257,7 +257,7 @@ int lu_dist_owner(Scene* s, int k, double* rhs, double* send, cudaStream_t st) {
     LLS_REQUIRE(k % P == s->cs.rank, LLS_ERR_ARG, "lu_dist_owner: this rank does not own block row k");
     const int ncols = nblk - 1 - k;
     lu_dist_owner_kernel<<<1 + ncols, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, k / P, ncols, rhs, send, s->uinv, s->lu_flags, s->lu_epoch,
-                                                                        s->scalars, s->status);
+                                                                        s->scalars, s->status, k + P >= nblk ? 1 : 0);
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
@@ -322,7 +322,8 @@ constexpr long long DIST_TIMEOUT_NS = 30LL * 1000 * 1000 * 1000;
 
 struct DistPeers {
     double* slots[DIST_MAX_P];
-    int* flags[DIST_MAX_P];
+    int* flags[DIST_MAX_P];       // "panel G complete" (diag image, y and every U tile have landed)
+    int* iflags[DIST_MAX_P];      // "diag image of panel G (+ y) has landed": all the L-panel tiles need
     int* progress[DIST_MAX_P];
     double* xbuf[DIST_MAX_P];
     int* xflags[DIST_MAX_P];
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_owner_p2p_kernel(double
             if (t < NB) pr.slots[q][slot_off + NB * TS + t] = dinv[t];
         }
         store_tile(gC, ld, sC);
-        pivot_guard<LU_THREADS>(sC, pl, k, ld / NB, scalars, status);
+        pivot_guard<LU_THREADS>(sC, pl, k < pr.P, k + pr.P >= ld / NB, scalars, status);
         if (rhs != nullptr && t < 32) {
             forward_rhs_warp(sC, rhs + (size_t)k * NB);
             __syncwarp();
@@ -639,11 +640,226 @@ __global__ void __launch_bounds__(NB) lu_dist_backsolve_p2p_kernel(const double*
     if (lb == 0 && t < bi) dist_wait(xfl + t, [token](int v) { return v == token; }, pr, status, nullptr);
 }
 
+
+// ---- one launch per block step and rank: trailing update with panel k, and panel k + 1 factored / solved / exchanged on the way ----
+// The single-GPU lu_step_kernel spread over the ranks.  Launch k of a rank covers ITS tiles of the trailing matrix (local block
+// rows with global index > k, block columns > k): every CTA does C -= L[i,k] U[k,j] (L from the rank's own rows, U from its
+// mailbox slot of panel k), then, by role,
+//   DIAG  (tile (k+1,k+1); only on the rank that owns block row k+1): factors it, stores the image (+ y_{k+1}) into the slot of
+//         panel k+1 of EVERY rank over NVLink and releases the image flags
+//   UROW  (tiles (k+1, j); owner only): waits for the image locally, solves U[k+1,j] = L11^-1 C, stores it into its own rows and
+//         into every rank's slot; the last of the owner's DIAG / UROW CTAs releases the "panel k+1 complete" flags everywhere
+//   LCOL  (tiles (i, k+1); every rank): waits for the image to land in ITS mailbox, solves L[i,k+1] = C U11^-1, b_i -= L[i,k+1] y_{k+1}
+//   OTHER stores C.
+// So the exchange of panel k+1 and every panel solve run underneath the DMMA bulk of step k; a launch waits for nothing but the
+// "panel k complete" flag that was released while launch k-1 was still running.  FIRST (k = -1): no update, panel 0 only.
+// Grid order: DIAG, UROW (owner only), LCOL, OTHER -- producers of a flag are resident before anything on this GPU can wait on it.
+// arrival of a whole panel: every owner CTA (1 DIAG + rem - 1 UROW) calls this from one thread AFTER fencing its stores at system
+// scope and synchronising; the last one to arrive releases the "panel complete" flags in every rank's mailbox
+__device__ __forceinline__ void dist_arrive(const DistPeers& pr, int rem, int Gn) {
+    const int done = atomicAdd(pr.counter, 1);
+    if (done == rem - 1) {
+        *reinterpret_cast<volatile int*>(pr.counter) = 0;
+        __threadfence_system();
+        for (int q = 0; q < pr.P; ++q) st_release_sys(pr.flags[q] + (Gn % DIST_RING), Gn + 1);
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __restrict__ Mloc, int ld, int k, int nblk, int lb0, int nloc,
+                                                                     double* __restrict__ rhs, DistPeers pr, int Gn,
+                                                                     double* __restrict__ uinv, double* __restrict__ scalars,
+                                                                     int* __restrict__ status) {
+    extern __shared__ __align__(16) double sm[];
+    double* sA = sm;
+    double* sB = sm + NB * TS;
+    __shared__ __align__(16) PivotLine pl;
+    __shared__ __align__(16) double dinv[NB];
+    __shared__ double yk[NB];
+    const int t = threadIdx.x, b = blockIdx.x;
+    const int P = pr.P, rank = pr.rank;
+    const int base = k + 1, rem = nblk - base;          // trailing matrix: block rows / columns base .. nblk - 1
+    const int Gc = Gn - 1;                              // global index of panel k (not FIRST)
+    if (b == 0 && t < P) st_release_sys(pr.progress[t] + rank, FIRST ? Gn : Gc);    // every global step below this one is consumed here
+    const bool own = (base % P == rank);                // this rank owns block row base: its local block lb0
+    enum { DIAG, UROW, LCOL, OTHER } role;
+    int lb, bj;
+    {
+        const int nd = own ? 1 : 0, nu = own ? rem - 1 : 0;
+        const int rows_below = nloc - nd;               // local block rows with global index > base
+        if (b < nd) { role = DIAG; lb = lb0; bj = base; }
+        else if (b < nd + nu) { role = UROW; lb = lb0; bj = base + 1 + (b - nd); }
+        else if (b < nd + nu + rows_below) { role = LCOL; lb = lb0 + nd + (b - nd - nu); bj = base; }
+        else {
+            const int o = b - nd - nu - rows_below;
+            if (rem <= 1 || o >= rows_below * (rem - 1)) return;       // nothing left for this rank: the launch only reported progress
+            role = OTHER; lb = lb0 + nd + o / (rem - 1); bj = base + 1 + o % (rem - 1);
+        }
+    }
+    const int bi = lb * P + rank;                       // global block row
+    double* gC = Mloc + (size_t)lb * NB * ld + (size_t)bj * NB;
+    constexpr int IMG2 = NB * TS / 2;
+    const size_t next_off = (size_t)(Gn % pr.S) * pr.slot_doubles;
+    double* mine = pr.slots[rank] + next_off;           // this rank's slot of panel k + 1
+    if (!FIRST) {
+        double acc[4][4][2];
+        {
+            double2 cn[4][4];
+            c_fetch(cn, gC, ld);
+            load_tile_async(sA, Mloc + (size_t)lb * NB * ld + (size_t)k * NB, ld);                                   // L[i,k]
+            if (t == 0) {
+                const int want = Gc + 1;
+                dist_wait(pr.flags[rank] + (Gc % DIST_RING), [want](int v) { return v == want; }, pr, status, b == 0 ? pr.stats : nullptr);
+            }
+            __syncthreads();
+            load_tile_async(sB, pr.slots[rank] + (size_t)(Gc % pr.S) * pr.slot_doubles + DIST_HDR + (size_t)(bj - base) * NB * NB, NB);   // U[k,j]
+            async_wait_all();
+            c_negate(acc, cn);
+        }
+        __syncthreads();
+        mma_tile(sA, sB, acc);
+        if (role == OTHER) {
+            acc_io<false>(acc, gC, ld);
+            return;
+        }
+        __syncthreads();
+        acc_io<false>(acc, sB, TS);
+        __syncthreads();
+    } else {
+        load_tile_async(sB, gC, ld);
+        async_wait_all();
+        __syncthreads();
+    }
+    double* sC = sB;
+    if (role == DIAG || role == UROW) {
+        // the slot of panel k + 1 may be rewritten once every rank has consumed its previous tenant (global step Gn - S)
+        if (t == 0 && Gn >= pr.S) {
+            const int need = Gn - pr.S + 1;
+            for (int q = 0; q < P; ++q)
+                if (q != rank) dist_wait(pr.progress[rank] + q, [need](int v) { return v >= need; }, pr, status, role == DIAG ? pr.stats + 1 : nullptr);
+        }
+        __syncthreads();
+    }
+    if (role == DIAG) {
+        factor_block(sC, pl);
+        if (t < NB) dinv[t] = 1.0 / sC[t * TS + t];
+        __syncthreads();
+        for (int e = t; e < NB * NB; e += LU_THREADS) {
+            const int r = e >> 6, c = e & 63;
+            const double v = sC[r * TS + c];
+            sA[r * TS + c] = (c > r) ? v * dinv[r] : v;
+        }
+        __syncthreads();
+        {   // own slot first: this rank's UROW CTAs are waiting for it
+            double2* g0 = reinterpret_cast<double2*>(mine);
+            const double2* s0 = reinterpret_cast<const double2*>(sA);
+#pragma unroll
+            for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
+            if (t < NB) mine[NB * TS + t] = dinv[t];
+        }
+        __threadfence();
+        __syncthreads();
+        if (t == 0) st_release(pr.own + (Gn % DIST_RING), Gn + 1);
+        for (int q = 0; q < P; ++q) {
+            if (q == rank) continue;
+            double2* g0 = reinterpret_cast<double2*>(pr.slots[q] + next_off);
+            const double2* s0 = reinterpret_cast<const double2*>(sA);
+#pragma unroll
+            for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
+            if (t < NB) pr.slots[q][next_off + NB * TS + t] = dinv[t];
+        }
+        if (t < 32) {       // y_{k+1} = L11^-1 b_{k+1}, part of the image every L-panel tile reads
+            forward_rhs_warp(sC, rhs + (size_t)base * NB);
+            __syncwarp();
+            const double y0 = rhs[(size_t)base * NB + t], y1 = rhs[(size_t)base * NB + 32 + t];
+            for (int q = 0; q < P; ++q) {
+                pr.slots[q][next_off + PUB_DOUBLES + t] = y0;
+                pr.slots[q][next_off + PUB_DOUBLES + 32 + t] = y1;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (t < P) st_release_sys(pr.iflags[t] + (Gn % DIST_RING), Gn + 1);
+        if (t == 0) dist_arrive(pr, rem, Gn);         // everything this CTA sends has been sent
+        // off the critical path of everybody else
+        store_tile(gC, ld, sC);
+        pivot_guard<LU_THREADS>(sC, pl, base < P, base + P >= nblk, scalars, status);
+        {   // inverse of U11 for the back substitution
+            const int ty = t >> 3, tx = t & 7;
+            double a[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = (ty + 16 * i == tx + 8 * j) ? 1.0 : 0.0;
+            panel_solve<false>(a, sA, dinv);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * TS + tx + 8 * j] = a[i][j];
+        }
+        __syncthreads();
+        store_tile(uinv + (size_t)base * NB * NB, NB, sC);
+    } else {
+        // panel roles: wait for the factored diagonal block of panel k + 1 (UROW: published locally by this launch's DIAG CTA;
+        // LCOL: landed in this rank's mailbox from wherever block row k + 1 lives)
+        if (t == 0) {
+            const int want = Gn + 1;
+            if (role == UROW) dist_wait(pr.own + (Gn % DIST_RING), [want](int v) { return v == want; }, pr, status, nullptr);
+            else dist_wait(pr.iflags[rank] + (Gn % DIST_RING), [want](int v) { return v == want; }, pr, status, nullptr);
+        }
+        __syncthreads();
+        {
+            const double2* g = reinterpret_cast<const double2*>(mine);
+            double2* sT2 = reinterpret_cast<double2*>(sA);
+            double2 v[IMG2 / LU_THREADS];
+#pragma unroll
+            for (int u = 0; u < IMG2 / LU_THREADS; ++u) v[u] = __ldcg(g + t + u * LU_THREADS);
+#pragma unroll
+            for (int u = 0; u < IMG2 / LU_THREADS; ++u) sT2[t + u * LU_THREADS] = v[u];
+            if (t < NB) {
+                dinv[t] = (role == UROW) ? 1.0 : __ldcg(mine + NB * TS + t);
+                if (role == LCOL) yk[t] = __ldcg(mine + PUB_DOUBLES + t);
+            }
+        }
+        __syncthreads();
+        const int ty = t >> 3, tx = t & 7;
+        const int sr = (role == UROW) ? 1 : TS, sc = (role == UROW) ? TS : 1;
+        double a[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc];
+        if (role == UROW) panel_solve<true>(a, sA, dinv);
+        else panel_solve<false>(a, sA, dinv);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc] = a[i][j];
+        __syncthreads();
+        store_tile(gC, ld, sC);
+        if (role == UROW) {
+            store_tile_all(pr, next_off + DIST_HDR + (size_t)(bj - base - 1) * NB * NB, sC);      // U[k+1,j] into every rank's slot
+        } else if (t < NB) {
+            double sdot = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < NB; ++q) sdot = fma(sC[t * TS + q], yk[q], sdot);
+            rhs[(size_t)bi * NB + t] -= sdot;
+        }
+    }
+    if (role == UROW) {
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) dist_arrive(pr, rem, Gn);
+    }
+}
+
 static size_t dist_align(size_t v) { return (v + 255) / 256 * 256; }
 
 // mailbox layout: [slots | xbuf | flags | progress | xflags | own | counter, abort | stats]
 struct DistLayout {
-    size_t slots, xbuf, flags, progress, xflags, own, misc, stats, total, slot_doubles;
+    size_t slots, xbuf, flags, iflags, progress, xflags, own, misc, stats, total, slot_doubles;
 };
 static DistLayout dist_layout(int ld, int S) {
     const int nblk = ld / NB;
@@ -653,6 +869,7 @@ static DistLayout dist_layout(int ld, int S) {
     L.slots = o;    o += dist_align((size_t)S * L.slot_doubles * 8);
     L.xbuf = o;     o += dist_align((size_t)ld * 8);
     L.flags = o;    o += dist_align((size_t)DIST_RING * 4);
+    L.iflags = o;   o += dist_align((size_t)DIST_RING * 4);
     L.progress = o; o += dist_align((size_t)DIST_MAX_P * 4);
     L.xflags = o;   o += dist_align((size_t)nblk * 4);
     L.own = o;      o += dist_align((size_t)DIST_RING * 4);
@@ -674,6 +891,7 @@ static void dist_fill_peers(Scene* s, DistComm* c, int S) {
         p.slots[q] = b ? reinterpret_cast<double*>(b + L.slots) : nullptr;
         p.xbuf[q] = b ? reinterpret_cast<double*>(b + L.xbuf) : nullptr;
         p.flags[q] = b ? reinterpret_cast<int*>(b + L.flags) : nullptr;
+        p.iflags[q] = b ? reinterpret_cast<int*>(b + L.iflags) : nullptr;
         p.progress[q] = b ? reinterpret_cast<int*>(b + L.progress) : nullptr;
         p.xflags[q] = b ? reinterpret_cast<int*>(b + L.xflags) : nullptr;
     }
@@ -725,6 +943,8 @@ int dist_comm_create(Scene* s, int slots, unsigned char* handle64) {
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_owner_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_panel_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         attr = true;
     }
     return LLS_OK;
@@ -798,6 +1018,32 @@ int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st) 
                                                                                pr.slots[rank] + (size_t)(G % S) * pr.slot_doubles + DIST_HDR);
         count_launch();
     };
+    static int fused_steps = -1;        // LLS_PARTITIONED_FUSED_STEPS=0: separate owner / panel / update launches with launch-order look-ahead
+    if (fused_steps < 0) {
+        const char* env = getenv("LLS_PARTITIONED_FUSED_STEPS");
+        fused_steps = (env != nullptr && env[0] == '0') ? 0 : 1;
+    }
+    if (fused_steps) {
+        for (int k = -1; k + 1 < nblk; ++k) {
+            const int base = k + 1, rem = nblk - base;
+            int lb0 = (base - rank + P - 1) / P;           // first local block whose global index lb * P + rank is >= base
+            if (lb0 < 0) lb0 = 0;
+            const int nloc = s->n_loc_blocks - lb0 > 0 ? s->n_loc_blocks - lb0 : 0;
+            const bool own = (base % P == rank);
+            const int nd = own ? 1 : 0, below = nloc - nd;
+            long long grid = nd + (own ? rem - 1 : 0) + below + (k >= 0 ? (long long)below * (rem - 1) : 0);
+            if (grid < 1) grid = 1;
+            const int Gn = (int)(G0 + base);
+            if (k < 0) {
+                lu_dist_step_kernel<true><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
+                                                                                             s->scalars, s->status);
+            } else {
+                lu_dist_step_kernel<false><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
+                                                                                              s->scalars, s->status);
+            }
+            count_launch();
+        }
+    } else {
     if (0 % P == rank) owner(0);
     for (int k = 0; k < nblk; ++k) {
         const int G = (int)(G0 + k);
@@ -815,6 +1061,7 @@ int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st) 
         } else {
             update(k, lb0, nloc);
         }
+    }
     }
     c->gstep = G0 + nblk;
     const int token = ++c->solves;

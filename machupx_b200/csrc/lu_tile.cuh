@@ -325,7 +325,9 @@ __device__ __forceinline__ void forward_rhs_warp(const double* __restrict__ sC, 
 // systems have pivot ratios of O(10)) and partial pivoting would have started to matter.
 constexpr double PIVOT_RATIO = 1e-6;
 template <int NT>
-__device__ __forceinline__ void pivot_guard(const double* __restrict__ sC, PivotLine& pl, int blk, int nblk, double* __restrict__ scalars,
+// `first` / `last`: this is the first / last diagonal block THIS rank factors in the factorisation (row-partitioned solve: every rank
+// guards the pivots of its own block rows, the host ORs the status words of the ranks).
+__device__ __forceinline__ void pivot_guard(const double* __restrict__ sC, PivotLine& pl, bool first, bool last, double* __restrict__ scalars,
                                             int* __restrict__ status) {
     const int t = threadIdx.x;
     if (t < NB) {
@@ -348,13 +350,13 @@ __device__ __forceinline__ void pivot_guard(const double* __restrict__ sC, Pivot
     panel_sync<NT>();
     if (t == 0) {
         double m = fmin(pl.piv[0], pl.piv[1]), M = fmax(pl.rcp[0], pl.rcp[1]);
-        if (blk > 0) {
+        if (!first) {
             m = fmin(m, scalars[1]);
             M = fmax(M, scalars[2]);
         }
         scalars[1] = m;
         scalars[2] = M;
-        if (blk == nblk - 1 && m < PIVOT_RATIO * M) atomicOr(status, LLS_STATUS_SMALL_PIVOT);
+        if (last && m < PIVOT_RATIO * M) atomicOr(status, LLS_STATUS_SMALL_PIVOT);
     }
 }
 

@@ -54,6 +54,15 @@ out = {"world": world, "control_points": scene._N, "ld": dev.ld, "aircraft": sce
        "CL_sum": float(sum(v["total"]["CL"] for v in FM.values())), "CD_sum": float(sum(v["total"]["CD"] for v in FM.values())),
        "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "phase_ms": tm,
        "fused_exchange": bool(dev.fused_exchange), "exchange_stats": dev.exchange_stats() if dev.fused_exchange else None}
+try:
+    off = ctypes.c_size_t(0) if "ctypes" in dir() else None
+    import ctypes as _ct
+    off = _ct.c_size_t(0)
+    dev.lib.lls_status_offset(dev.handle, _ct.byref(off))
+    sc = dev.d_work[off.value - 256: off.value - 256 + 32].view(torch.float64).cpu().numpy()
+    out["pivot_min_max"] = [float(sc[1]), float(sc[2])]
+except Exception as e:
+    out["pivot_min_max"] = repr(e)
 if check_rows > 0:
     from oracle import lls_oracle as O      # checker only
     T = O.Tables(scene._tables, build_aircraft_state(scene)); F = O.flow_state(T)
