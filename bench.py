@@ -182,7 +182,7 @@ def cpu_sample(tables, ac_state, meta, threads):
     return 1.0 / total, total, parts
 
 
-def reference_solve(workload_input, all_cores=True, solves=1, timeout=3000):
+def reference_solve(workload_input, all_cores=True, solves=1, timeout=3000, sweep_states=None):
     """Runs oracle/ref_runner.py (the UNMODIFIED reference staged in oracle/_ref + the stand-ins of oracle/ref_stubs) in its own
     process on ``workload_input`` and returns its JSON, or {"unavailable": why}."""
     import tempfile
@@ -198,8 +198,15 @@ def reference_solve(workload_input, all_cores=True, solves=1, timeout=3000):
     with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
         json.dump(workload_input, fh)
         path = fh.name
+    spath = None
+    if sweep_states is not None:
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+            json.dump(sweep_states, fh)
+            spath = fh.name
     try:
         cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), path, "--solves", str(solves)] + (["--all-cores-too"] if all_cores else [])
+        if spath is not None:
+            cmd += ["--sweep", spath]
         env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS")}
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
         lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -208,6 +215,8 @@ def reference_solve(workload_input, all_cores=True, solves=1, timeout=3000):
         return json.loads(lines[-1])
     finally:
         os.unlink(path)
+        if spath is not None:
+            os.unlink(spath)
 
 
 def swarm_port_estimate(n, iters, threads):
@@ -246,6 +255,33 @@ def run_reference(args):
                                  "seconds_per_solve_extrapolated": est, "parts_at_n4000": parts, "reference": "out of memory"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "ms_per_step is the wall time of the sample this run measured, not the extrapolated solve (value = 1 / extrapolated seconds)"}
+        print(json.dumps(line))
+        return
+    if workload == "c3":
+        import copy
+        import api_scenarios as S
+        with open(os.path.join(ROOT, "tests", "golden", "api_scenarios.json")) as fh:
+            gold = json.load(fh)["c3"]
+        inp = copy.deepcopy(gold["input"])
+        inp["solver"]["type"] = args.c3_solver
+        inp["solver"].pop("relaxation", None)
+        states = S.c3_states(S.C3_SUB, S.C3_SUB)
+        ref = reference_solve(inp, all_cores=False, sweep_states=states)
+        if "unavailable" in ref:
+            print(json.dumps({"impl": "reference", "unavailable": ref["unavailable"]}))
+            return
+        sw = ref["sweep"]
+        value = sw["cases_per_second"]
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "steps_requested": args.steps,
+                "warmup": 0, "ms_per_step": sw["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "FlyingWing alpha/beta sweep (BASELINE.json configs[2]), %s solver: the reference's serial "
+                                       "set_aircraft_state -> solve_forces loop" % args.c3_solver, "control_points": int(ref["control_points"]),
+                           "cases": 4096, "solver": {"type": args.c3_solver}},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                                 "sample": "UNMODIFIED reference (oracle/_ref): the 8 x 8 sub-grid (64 of the 4,096 states) of the sweep, serial loop, "
+                                           "as shipped (1 BLAS thread); %.1f s" % sw["seconds"], "host_cores": int(ref["cores"])},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
     tables, ac_state, g, meta = load_workload(workload)
@@ -439,9 +475,122 @@ def run_ours_swarm(args):
         dist.destroy_process_group()
 
 
+def run_ours_c3(args):
+    """BASELINE.json configs[2]: the 64 x 64 alpha / beta sweep of examples/FlyingWing (4,096 flight states of a 180-point scene),
+    sharded by case over the ranks (no data-path collective, one all_gather of the totals), every shard ONE batched device pass.
+    A step = the whole sweep; value / e2e are solves (cases) per second.  Strong scaling: 4,096 cases at every N."""
+    import copy
+    import warnings
+    import torch
+    import torch.distributed as dist
+    import api_scenarios as S
+    from machupx_b200 import _native
+    from machupx_b200.sweep import BatchSceneSolver, run_sweep, shard_cases
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    with open(os.path.join(ROOT, "tests", "golden", "api_scenarios.json")) as fh:
+        gold = json.load(fh)["c3"]
+    inp = copy.deepcopy(gold["input"])
+    inp["solver"]["type"] = args.c3_solver
+    inp["solver"].pop("relaxation", None)
+    solver = BatchSceneSolver(inp)
+    states = S.c3_states()
+    lib = _native.load()
+
+    def step():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return run_sweep(states, solver, on_not_converged="nan")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        table, its, ok = step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = lib.lls_launch_count()
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        table, its, ok = step()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    dev_ms = e0.elapsed_time(e1)
+    launches = lib.lls_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # device-only pass: the rank's shard with the state blocks already in HBM
+    bdev = solver.scene._batch_device
+    sc = solver.scene
+    e0.record()
+    for _ in range(args.steps):
+        bdev.solve(sc._solver_type, sc._solver_convergence, sc._solver_relaxation, sc._max_solver_iterations, sc._impingement_threshold)
+    e1.record()
+    barrier()
+    res_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms, res_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, res_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ncases = len(states)
+    # parity against the reference's serial loop on the 8 x 8 sub-grid (tests/golden/api_scenarios.json)
+    from machupx_b200.sweep import TOTAL_KEYS
+    parity = None
+    if args.c3_solver in gold:
+        pick = [64 * a + b for a in gold["alpha_idx"] for b in gold["beta_idx"]]
+        ref = np.array([[c[k] for k in TOTAL_KEYS] for c in gold[args.c3_solver]["totals"]])
+        err = float(np.abs(table[pick] - ref).max() / max(1.0, np.abs(ref).max()))
+        parity = {"max_rel_err_vs_reference_on_8x8_subgrid": err,
+                  "newton_iterations_equal": bool(args.c3_solver != "nonlinear" or [int(x) for x in its[pick]] == gold["nonlinear"]["iterations"]),
+                  "newton_iterations_min_max": [int(its.min()), int(its.max())], "all_converged": bool(ok.all())}
+    lo, hi = shard_cases(ncases, world, 0)
+    line = {
+        "metric": METRIC, "value": ncases * args.steps / (res_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": res_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "FlyingWing alpha/beta sweep: 64 x 64 = 4,096 flight states (alpha -2..10 deg, beta -6..6 deg, V = 100) of the "
+                               "180-control-point examples/FlyingWing scene, %s solver, sharded by case over the GPUs "
+                               "(BASELINE.json configs[2]); a step is the whole sweep, value counts solves (cases)" % args.c3_solver,
+                   "control_points": int(sc._N), "cases": ncases, "cases_per_rank": hi - lo, "solver": {"type": args.c3_solver},
+                   "l2_policy": "per-rank working set (V_ji + J of the shard: %.1f GB) exceeds the 126 MB L2; no explicit flush" % (
+                       (hi - lo) * (sc._N * 3 + 192) * 192 * 8 / 1e9)},
+        "e2e": {"value": ncases * args.steps / (wall_ms * 1e-3), "unit": UNIT, "ms_per_step": wall_ms / args.steps,
+                "h2d_bytes_per_step": int((hi - lo) * 16 * 8), "d2h_bytes_per_step": int((hi - lo) * (sc._tables["n_segments"] * 12 * 8 + 20)),
+                "note": "public API: sweep.run_sweep -> Scene.solve_forces_batch per rank (state blocks built on the host, pinned copy in, "
+                        "segment sums / iterations / status out) + one all_gather of the totals"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"kernel": "lu_small_case_kernel: one CTA factors and solves one case (3 block rows), DMMA trailing updates",
+                     "bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                     "note": "latency-bound small systems; see DESIGN.md section 6.1"},
+        "parity": parity, "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     if pick_workload(args) == "swarm":
         return run_ours_swarm(args)
+    if pick_workload(args) == "c3":
+        return run_ours_c3(args)
     args.workload = pick_workload(args)
     import torch
     import torch.distributed as dist
@@ -643,7 +792,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "testplane", "swarm800", "swarm"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "testplane", "swarm800", "swarm"])
+    ap.add_argument("--c3-solver", default="nonlinear", choices=["nonlinear", "linear"])
     ap.add_argument("--swarm-aircraft", type=int, default=32)
     ap.add_argument("--swarm-grid", type=int, default=200)
     ap.add_argument("--force-partitioned", action="store_true", help="swarm on one GPU through the partitioned kernels")

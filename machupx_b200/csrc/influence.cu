@@ -15,6 +15,7 @@
 //
 // FP64-pipe bound by design: 24 B written per pair against ~0.5 kflop of DFMA-class work.
 #include <cfloat>
+#include <cstdlib>
 #include "lls_internal.h"
 #include "section.cuh"
 
@@ -131,7 +132,17 @@ constexpr int kInfUnroll = INF_UNROLL;   // rows per trip of the control-point l
 #ifndef INF_MIN_BLOCKS
 #define INF_MIN_BLOCKS 4   // 128 registers: 16 warps per SM; measured 0.61 ms vs 0.76 ms at 2 blocks (C2), slower again at 5-6 (spills)
 #endif
-__global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kernel(
+#ifndef INF_PLAIN_MIN_BLOCKS
+#define INF_PLAIN_MIN_BLOCKS 5   // the plain specialisation carries no blend state: 102 registers -> 20 warps per SM
+#endif
+// Two specialisations share the grid (INF_SPLIT, the default).  A tile (64 control points x 4 windows of vortices) whose rows and
+// vortices cannot lie on a common wing -- wings are contiguous index ranges, so that is an interval test on two table entries --
+// is PLAIN: cross-wing / cross-aircraft pairs, about two thirds of a refined aeroplane and nearly all of a swarm.  Its kernel has no
+// blend code at all, hence no blend registers: more resident warps for the dependent FP64 chains of the reciprocals and square roots.
+// The other tiles take the BLEND kernel (the general one).  Each launch covers the whole grid and a CTA whose tile belongs to the other
+// specialisation returns at once.  MODE: 0 = general kernel for every tile (INF_SPLIT=0), 1 = blend tiles only, 2 = plain tiles only.
+template <int MODE>
+__global__ void __launch_bounds__(INF_WARPS * 32, MODE == 2 ? INF_PLAIN_MIN_BLOCKS : INF_MIN_BLOCKS) influence_kernel(
     int n, int ld, const double* __restrict__ tab, const int32_t* __restrict__ itab, const double* __restrict__ ac,
     const double* __restrict__ out, double* __restrict__ V, double thr, int* __restrict__ status, CaseStrides cs) {
     tab = case_ptr(tab, cs.tab);
@@ -146,6 +157,14 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
     const int row0 = global_row(cs, lrow0);           // ... and in the scene
     const int nrows = min(INF_ROWS, n - row0);
     if (nrows <= 0) return;
+    if (MODE != 0) {
+        // wings spanned by the rows of this chunk: [wing begin of the first row, wing end of the last row); vortices of this CTA:
+        // [first window's first lane, last window's last lane]
+        const int wlo = itab[(size_t)LLS_I_WING_BEGIN * ld + row0], whi = itab[(size_t)LLS_I_WING_END * ld + row0 + nrows - 1];
+        const int jlo = blockIdx.x * INF_WARPS * INF_OUT - 1, jhi = (blockIdx.x * INF_WARPS + INF_WARPS) * INF_OUT;
+        const bool may_blend = (jlo < whi) && (jhi >= wlo);
+        if (may_blend != (MODE == 1)) return;
+    }
 
     // stage the row constants of this chunk
     for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
@@ -207,7 +226,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
             q1 = P1;
         }
 
-        if (__any_sync(0xffffffffu, blended)) {
+        if (MODE != 2 && __any_sync(0xffffffffu, blended)) {
             const Vec3 pcd{rs.pcd[0][r], rs.pcd[1][r], rs.pcd[2][r]};
             const double sigma = rs.sigma[r], span_i = rs.span[r];
             const int we_i = rs.we[r];
@@ -282,9 +301,22 @@ __global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_BLOCKS) influence_kern
 int launch_influence(Scene* s, double impingement_threshold, cudaStream_t st) {
     const int windows = (s->ld + INF_OUT - 1) / INF_OUT;
     dim3 grid((windows + INF_WARPS - 1) / INF_WARPS, s->n_loc_blocks, s->ncases);
-    influence_kernel<<<grid, INF_WARPS * 32, 0, st>>>(s->n, s->ld, s->tab, s->itab, s->ac, s->out, s->V, impingement_threshold, s->status,
-                                                      strides(s, false));
-    count_launch();
+    static int split = -1;      // INF_SPLIT=0: one general kernel for every tile
+    if (split < 0) {
+        const char* env = getenv("INF_SPLIT");
+        split = (env != nullptr && env[0] == '0') ? 0 : 1;
+    }
+    if (split) {
+        influence_kernel<2><<<grid, INF_WARPS * 32, 0, st>>>(s->n, s->ld, s->tab, s->itab, s->ac, s->out, s->V, impingement_threshold, s->status,
+                                                             strides(s, false));
+        influence_kernel<1><<<grid, INF_WARPS * 32, 0, st>>>(s->n, s->ld, s->tab, s->itab, s->ac, s->out, s->V, impingement_threshold, s->status,
+                                                             strides(s, false));
+        count_launch(2);
+    } else {
+        influence_kernel<0><<<grid, INF_WARPS * 32, 0, st>>>(s->n, s->ld, s->tab, s->itab, s->ac, s->out, s->V, impingement_threshold, s->status,
+                                                             strides(s, false));
+        count_launch();
+    }
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
 }

@@ -66,7 +66,7 @@ __device__ __forceinline__ void chain_yield(const ChainGuard& g) {        // upd
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(g.diag_sm) : "memory");
     if (v == g.tag) {
-        while (ld_acquire(g.flag) != g.epoch) __nanosleep(128);
+        while (ld_acquire(g.flag) < pub_token(g.epoch, PUB_GROUPS)) __nanosleep(128);
     }
 }
 
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
                                                                 double* __restrict__ uinv, int* __restrict__ flags, int epoch,
                                                                 double* __restrict__ scalars, int* __restrict__ status, CaseStrides cs,
                                                                 int* __restrict__ counters, int chunk, int nworkers, int* __restrict__ diag_sm,
-                                                                int* __restrict__ claims, int panel_sms, int inv_block) {
+                                                                int* __restrict__ claims, int panel_sms, int inv_block, int pipe) {
     constexpr int NT = WORKERS ? 256 : LU_THREADS;   // threads per CTA; the panel roles always run on threads 0..127
     static_assert(!(WORKERS && (FIRST || PASSES != 1)), "workers take one panel per visit");
     static_assert(SPLIT == 1 || SPLIT == 2 || SPLIT == 4, "CTAs per panel tile");
@@ -383,7 +383,9 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
 
     if (role == DIAG) {
         LU_CLK(3);
-        factor_block<NT>(sC, pl);
+        // pipe: the factors are published group by group from inside the factorisation (lu_tile.cuh), the panel CTAs trail it
+        if (pipe) factor_block<NT, true>(sC, pl, img, flags + blk, epoch);
+        else factor_block<NT>(sC, pl);
         LU_CLK(4);
         if (t < NB) dinv[t] = 1.0 / sC[t * TS + t];
         panel_sync<NT>();
@@ -393,26 +395,28 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
             sA[r * TS + c] = (c > r) ? v * dinv[r] : v;
         }
         panel_sync<NT>();
-        {
+        if (!pipe) {
             double2* g0 = reinterpret_cast<double2*>(img);
             const double2* s0 = reinterpret_cast<const double2*>(sA);
 #pragma unroll
             for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
             if (t < NB) img[NB * TS + t] = dinv[t];
+            __threadfence();
+            panel_sync<NT>();
+            if (t == 0) st_release(flags + blk, pub_token(epoch, PUB_GROUPS));
         }
-        __threadfence();
-        panel_sync<NT>();
-        if (t == 0) st_release(flags + blk, epoch);
         LU_CLK(5);
         // everything below is off the critical path of the panel CTAs
         store_tile(gC, ld, sC);
         pivot_guard<NT>(sC, pl, blk == 0, blk == ld / NB - 1, scalars, status);
         if (rhs != nullptr && t < 32) forward_rhs_warp(sC, rhs + (size_t)blk * NB);
         // W = U11, pre-scaled rows in sA: the solve below turns the identity into inv(U11) (unless an INV CTA does that)
+    } else if (pipe) {
+        if (t < NB) dinv[t] = 1.0;      // U-panel tiles: unit diagonal; L-panel tiles / inverse: overwritten group by group
     } else {
         // panel roles: wait for the factored diagonal block
         if (t == 0) {
-            while (ld_acquire(flags + blk) != epoch) __nanosleep(32);
+            while (ld_acquire(flags + blk) < pub_token(epoch, PUB_GROUPS)) __nanosleep(32);
         }
         panel_sync<NT>();
         const double2* g = reinterpret_cast<const double2*>(img);
@@ -447,7 +451,10 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
                 for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * sr + (tx + 8 * j) * sc];
         }
         LU_CLK(6);
-        if (role == UROW) panel_solve<true>(a, sA, dinv);
+        if (pipe && role != DIAG) {
+            if (role == UROW) panel_solve_piped<true, 4, NT>(a, sA, dinv, img, flags + blk, epoch);
+            else panel_solve_piped<false, 4, NT>(a, sA, dinv, img, flags + blk, epoch);
+        } else if (role == UROW) panel_solve<true>(a, sA, dinv);
         else panel_solve<false>(a, sA, dinv);
         LU_CLK(7);
         panel_sync<NT>();   // everyone is done reading the tile (and, in the diag CTA, the factors for the right-hand side)
@@ -465,7 +472,10 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
             for (int j = 0; j < 8; ++j)
                 a[i][j] = (role == INV) ? ((r0 + 16 * i == tx + 8 * j) ? 1.0 : 0.0) : sC[(r0 + 16 * i) * sr + (tx + 8 * j) * sc];
         LU_CLK(6);
-        if (role == UROW) panel_solve<true, RI>(a, sA, dinv);
+        if (pipe) {
+            if (role == UROW) panel_solve_piped<true, RI, NT>(a, sA, dinv, img, flags + blk, epoch);
+            else panel_solve_piped<false, RI, NT>(a, sA, dinv, img, flags + blk, epoch);
+        } else if (role == UROW) panel_solve<true, RI>(a, sA, dinv);
         else panel_solve<false, RI>(a, sA, dinv);
         LU_CLK(7);
         panel_sync<NT>();
@@ -500,6 +510,162 @@ __global__ void __launch_bounds__(WORKERS ? 256 : LU_THREADS, WORKERS ? 2 : 3) l
         ChainGuard none = guard;
         none.diag_sm = nullptr;       // the panel of this launch is done
         lu_update_worker<NT>(geom, counters + base, chunk, sm, wsh, none);
+    }
+}
+
+
+// ---- small systems in large batches: one CTA factors and solves one case ---------------------------------------------------------
+// BASELINE.json configs[2] (FlyingWing sweep: 4,096 flight states of a 180-point scene, ld = 192 = 3 block rows).  The general
+// kernel gives every tile of every case a CTA and lets the panel CTAs spin on their case's diagonal block: four out of five resident
+// CTAs are waiting at any time.  Here ONE 128-thread CTA walks through the whole right-looking factorisation of its case (diagonal
+// factorisation, U block row, L block column with the right-hand side, DMMA trailing update, tiles through the L2) and then through
+// the back substitution with the U blocks themselves (no inverse diagonal blocks needed): nothing ever waits for another CTA, and the
+// three CTAs an SM holds keep its FP64 pipe busy with three different cases.
+constexpr int SMALL_MAX_NBLK = 4;
+
+// x = U^-1 b for the upper-triangular factor held row-major in sU (row stride TS); warp 0 only, lane l keeps entries l and l + 32
+__device__ __forceinline__ void backward_warp(const double* __restrict__ sU, double* __restrict__ b) {
+    const int lane = threadIdx.x;
+    double x0 = b[lane], x1 = b[lane + 32];
+    const double d0 = 1.0 / sU[lane * TS + lane], d1 = 1.0 / sU[(lane + 32) * TS + lane + 32];
+#pragma unroll 1
+    for (int q = NB - 1; q >= 0; --q) {
+        // x_q is final once every column right of q has been folded in: scale it where it lives, then broadcast
+        if (q >= 32) { if (lane == q - 32) x1 *= d1; } else { if (lane == q) x0 *= d0; }
+        const double xq = __shfl_sync(0xffffffffu, (q < 32) ? x0 : x1, q & 31);
+        if (lane < q) x0 = fma(-sU[lane * TS + q], xq, x0);
+        if (lane + 32 < q) x1 = fma(-sU[(lane + 32) * TS + q], xq, x1);
+    }
+    b[lane] = x0;
+    b[lane + 32] = x1;
+}
+
+__global__ void __launch_bounds__(LU_THREADS, 3) lu_small_case_kernel(double* __restrict__ M, int ld, int nblk, double* __restrict__ rhs,
+                                                                      double* __restrict__ x, double* __restrict__ scalars,
+                                                                      int* __restrict__ status, CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    M = case_ptr(M, cs.M);
+    rhs = case_work_ptr(rhs, cs.work);
+    x = case_work_ptr(x, cs.work);
+    scalars = case_work_ptr(scalars, cs.work);
+    status = case_work_ptr(status, cs.work);
+    extern __shared__ __align__(16) double sm[];
+    double* sA = sm;                 // image of the factored diagonal block / L operand
+    double* sB = sm + NB * TS;       // working tile / U operand
+    __shared__ __align__(16) PivotLine pl;
+    __shared__ __align__(16) double dinv[NB];
+    __shared__ __align__(16) double vec[NB];
+    const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
+    auto tile = [&](int bi, int bj) { return M + (size_t)bi * NB * ld + (size_t)bj * NB; };
+    for (int k = 0; k < nblk; ++k) {
+        // diagonal block: factor, keep the pre-scaled image in sA
+        load_tile_async(sB, tile(k, k), ld);
+        async_wait_all();
+        __syncthreads();
+        factor_block(sB, pl);
+        if (t < NB) dinv[t] = 1.0 / sB[t * TS + t];
+        __syncthreads();
+        for (int e = t; e < NB * NB; e += LU_THREADS) {
+            const int r = e >> 6, c = e & 63;
+            const double v = sB[r * TS + c];
+            sA[r * TS + c] = (c > r) ? v * dinv[r] : v;
+        }
+        store_tile(tile(k, k), ld, sB);
+        pivot_guard<LU_THREADS>(sB, pl, k == 0, k == nblk - 1, scalars, status);
+        if (t < 32) forward_rhs_warp(sB, rhs + (size_t)k * NB);          // y_k
+        __syncthreads();
+        if (t < NB) vec[t] = rhs[(size_t)k * NB + t];
+        // U block row: U[k,j] = L11^-1 A[k,j] (transposed problem: W = L11^T, unit diagonal)
+        for (int j = k + 1; j < nblk; ++j) {
+            __syncthreads();
+            load_tile_async(sB, tile(k, j), ld);
+            async_wait_all();
+            __syncthreads();
+            double a[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) a[i][jj] = sB[(ty + 16 * i) + (tx + 8 * jj) * TS];
+            panel_solve<true>(a, sA, dinv);          // (unit diagonal: dinv is not read)
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) sB[(ty + 16 * i) + (tx + 8 * jj) * TS] = a[i][jj];
+            __syncthreads();
+            store_tile(tile(k, j), ld, sB);
+        }
+        // L block column: L[i,k] = A[i,k] U11^-1, b_i -= L[i,k] y_k
+        for (int i2 = k + 1; i2 < nblk; ++i2) {
+            __syncthreads();
+            load_tile_async(sB, tile(i2, k), ld);
+            async_wait_all();
+            __syncthreads();
+            double a[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) a[i][jj] = sB[(ty + 16 * i) * TS + tx + 8 * jj];
+            panel_solve<false>(a, sA, dinv);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) sB[(ty + 16 * i) * TS + tx + 8 * jj] = a[i][jj];
+            __syncthreads();
+            store_tile(tile(i2, k), ld, sB);
+            if (t < NB) {
+                double sdot = 0.0;
+#pragma unroll 8
+                for (int q = 0; q < NB; ++q) sdot = fma(sB[t * TS + q], vec[q], sdot);
+                rhs[(size_t)i2 * NB + t] -= sdot;
+            }
+        }
+        // trailing update on the FP64 tensor path: A[i,j] -= L[i,k] U[k,j]
+        for (int i2 = k + 1; i2 < nblk; ++i2) {
+            for (int j = k + 1; j < nblk; ++j) {
+                __syncthreads();          // the tiles just stored by this CTA are visible to it; the operand slots are free
+                double acc[4][4][2];
+                {
+                    double2 cn[4][4];
+                    c_fetch(cn, tile(i2, j), ld);
+                    if (j == k + 1) load_tile_async(sA, tile(i2, k), ld);      // the L operand stays for the whole tile row
+                    load_tile_async(sB, tile(k, j), ld);
+                    async_wait_all();
+                    c_negate(acc, cn);
+                }
+                __syncthreads();
+                mma_tile(sA, sB, acc);
+                acc_io<false>(acc, tile(i2, j), ld);
+            }
+        }
+        __syncthreads();
+    }
+    // back substitution: x_k = U_kk^-1 (y_k - sum_{j > k} U[k,j] x_j), block rows from the last to the first
+    for (int k = nblk - 1; k >= 0; --k) {
+        double s0 = (t < NB) ? rhs[(size_t)k * NB + t] : 0.0;
+        for (int j = k + 1; j < nblk; ++j) {
+            __syncthreads();
+            load_tile_async(sB, tile(k, j), ld);
+            if (t < NB) vec[t] = x[(size_t)j * NB + t];
+            async_wait_all();
+            __syncthreads();
+            if (t < NB) {
+                double sdot = 0.0;
+#pragma unroll 8
+                for (int q = 0; q < NB; ++q) sdot = fma(sB[t * TS + q], vec[q], sdot);
+                s0 -= sdot;
+            }
+        }
+        __syncthreads();
+        load_tile_async(sB, tile(k, k), ld);
+        if (t < NB) vec[t] = s0;
+        async_wait_all();
+        __syncthreads();
+        if (t < 32) backward_warp(sB, vec);
+        __syncthreads();
+        if (t < NB) x[(size_t)k * NB + t] = vec[t];
+        __threadfence_block();
     }
 }
 
@@ -629,6 +795,8 @@ static int g_pack_min_rem = 0;        // LLS_LU_PACK_MIN_REM: trailing matrices 
 static int g_split4_max_rem = 8;      // LLS_LU_SPLIT4_MAX_REM: ... and four CTAs per panel tile up to this (N = 200 0.107 -> 0.103 ms, N = 1000 0.432 -> 0.422 ms; slower again from 16 up)
 static int g_split_max_rem = 36;      // LLS_LU_SPLIT_MAX_REM: trailing matrices of at most this many block rows use two CTAs per panel tile (0 = never)
 static bool g_lu_inv_cta = true;      // LLS_LU_INV_CTA=0: the diag CTA inverts U11 itself after publishing
+static int g_small_batch_min = 16;    // LLS_LU_SMALL_BATCH_MIN: batches of at least this many cases of at most 4 block rows take the one-CTA-per-case kernel (0 = never)
+static int g_lu_pipe = 0;             // LLS_LU_PIPE=1: the diag CTA publishes its factors group by group from inside the factorisation and the panel solves trail it (lu_tile.cuh).  Correct, measured SLOWER on B200 (N = 4000: 2.78 -> 2.84 ms, N = 1000: 0.429 -> 0.457 ms): eight extra fences / barriers / scattered stores in the factorisation and eight flag round trips in every panel CTA cost more than the ~13 k cycles of overlap return; off by default
 static bool g_lu_pdl = true;          // LLS_LU_PDL=0: plain stream-ordered launches of the block steps
 
 template <class... KArgs, class... Args>
@@ -664,6 +832,10 @@ static int lu_prepare(Scene* s) {
         if (env != nullptr) g_split_max_rem = atoi(env);
         env = getenv("LLS_LU_INV_CTA");
         if (env != nullptr && env[0] == '0') g_lu_inv_cta = false;
+        env = getenv("LLS_LU_SMALL_BATCH_MIN");
+        if (env != nullptr) g_small_batch_min = atoi(env);
+        env = getenv("LLS_LU_PIPE");
+        if (env != nullptr) g_lu_pipe = atoi(env) ? 1 : 0;
         env = getenv("LLS_LU_PDL");
         if (env != nullptr && env[0] == '0') g_lu_pdl = false;
         env = getenv("LLS_LU_CHAIN_GUARD");
@@ -675,6 +847,7 @@ static int lu_prepare(Scene* s) {
         int dev = 0;
         LLS_CUDA_TRY(cudaGetDevice(&dev));
         LLS_CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_small_case_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_step_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
@@ -708,6 +881,12 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     const int ncases = (M == s->M) ? s->ncases : 1;
     const CaseStrides cs = (M == s->M) ? strides(s, masked) : CaseStrides();
     LLS_TRY(lu_prepare(s));
+    if (ncases > 1 && rhs != nullptr && nblk <= SMALL_MAX_NBLK && g_small_batch_min > 0 && ncases >= g_small_batch_min) {
+        lu_small_case_kernel<<<dim3(1, 1, ncases), LU_THREADS, 2 * TILE_BYTES, st>>>(M, ld, nblk, rhs, x, s->scalars, s->status, cs);
+        count_launch();
+        LLS_CUDA_TRY(cudaGetLastError());
+        return LLS_OK;
+    }
     const int epoch = ++s->lu_epoch;
     double* dbuf = s->inv;          // 2 x PUB_DOUBLES published diagonal factors
     int* flags = s->lu_flags;
@@ -718,6 +897,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
     // one more CTA per launch inverts U11 (see the INV role); not in a batch, where other cases hide one case's chain and a CTA more
     // per case and launch is only overhead (C3 sweep: 39.6 k -> 36.9 k cases/s with it)
     const int inv_cta = (g_lu_inv_cta && ncases == 1) ? 1 : 0;
+    const int pipe = (g_lu_pipe && ncases == 1) ? 1 : 0;      // a batch hides one case's chain behind the other cases
     const bool split_ok = (ncases == 1);           // a batch hides the chain of one case behind the other cases: no redundant tile updates there
     {
         const int rem = nblk;       // block 0 and its panel
@@ -725,17 +905,17 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             const int roles = 1 + 8 * (rem - 1);
             LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false, 4>, dim3(roles + 4 * inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                     M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
-                    inv_cta ? roles : -1));
+                    inv_cta ? roles : -1, pipe));
         } else if (split_ok && rem <= g_split_max_rem) {
             const int roles = 1 + 4 * (rem - 1);
             LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false, 2>, dim3(roles + 2 * inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                     M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
-                    inv_cta ? roles : -1));
+                    inv_cta ? roles : -1, pipe));
         } else {
             const int grid = 2 * rem - 1;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<true, 1, false>, dim3(grid + inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                     M, ld, -1, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, workers_ok ? counters : nullptr, 0, 0, diag_sm, claims, 0,
-                    inv_cta ? grid : -1));
+                    inv_cta ? grid : -1, pipe));
         }
         count_launch();
     }
@@ -749,7 +929,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             if (nworkers > chunks) nworkers = chunks;
             if (nworkers < 1) nworkers = 1;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, true>, dim3(2 * rem - 1 + (int)nworkers, 1, 1), 256, (size_t)3 * TILE_BYTES, st,
-                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8), (int)nworkers, diag_sm, nullptr, 0, -1));
+                M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, counters, g_worker_chunk | (g_worker_dbg << 8), (int)nworkers, diag_sm, nullptr, 0, -1, pipe));
             count_launch();
             k += 1;
             continue;
@@ -760,7 +940,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             // thin launch: block row / column k+1 only (update with panel k, factor panel k+1) ...
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(2 * rem - 1 + inv_cta, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                 M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0,
-                inv_cta ? 2 * rem - 1 : -1));
+                inv_cta ? 2 * rem - 1 : -1, pipe));
             count_launch();
             // ... then one visit of the rest with panels k and k+1 together, factoring panel k+2 on the way
             const int rem2 = rem - 1;
@@ -768,7 +948,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             const int inv2 = psm2 ? 0 : inv_cta;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 2, false>, dim3(rem2 * rem2 + inv2, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                 M, ld, k, rem2, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm2 ? claims : nullptr, psm2,
-                inv2 ? 2 * rem2 - 1 : -1));
+                inv2 ? 2 * rem2 - 1 : -1, pipe));
             count_launch();
             k += 2;
         } else {
@@ -779,10 +959,10 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
                 const dim3 grid(roles + parts * inv_cta + (rem - 1) * (rem - 1), 1, ncases);
                 if (parts == 4) {
                     LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false, 4>, grid, LU_THREADS, (size_t)2 * TILE_BYTES, st, M, ld, k, rem, rhs, dbuf,
-                        s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0, inv_cta ? roles : -1));
+                        s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0, inv_cta ? roles : -1, pipe));
                 } else {
                     LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false, 2>, grid, LU_THREADS, (size_t)2 * TILE_BYTES, st, M, ld, k, rem, rhs, dbuf,
-                        s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0, inv_cta ? roles : -1));
+                        s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, nullptr, 0, inv_cta ? roles : -1, pipe));
                 }
                 count_launch();
                 k += 1;
@@ -791,7 +971,7 @@ int lu_factor_solve(Scene* s, double* M, double* rhs, double* x, cudaStream_t st
             const int inv1 = psm ? 0 : inv_cta;
             LLS_CUDA_TRY(launch_step(lu_step_kernel<false, 1, false>, dim3(rem * rem + inv1, 1, ncases), LU_THREADS, (size_t)2 * TILE_BYTES, st,
                 M, ld, k, rem, rhs, dbuf, s->uinv, flags, epoch, s->scalars, s->status, cs, nullptr, 0, 0, diag_sm, psm ? claims : nullptr, psm,
-                inv1 ? 2 * rem - 1 : -1));
+                inv1 ? 2 * rem - 1 : -1, pipe));
             count_launch();
             k += 1;
         }

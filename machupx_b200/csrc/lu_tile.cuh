@@ -225,14 +225,78 @@ __device__ __forceinline__ void factor_group(double (&a)[4][8], PivotLine& pl, i
     }
 }
 
-template <int NT = LU_THREADS>
-__device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine& pl) {
+// ---- pipelined publication of the factored diagonal block ---------------------------------------------------------------------
+// The panel solves consume the factors in the same order the factorisation produces them: group J of a solve (pivots 8 J .. 8 J + 7)
+// needs rows 8 J .. of U11 (L-panel tiles) or columns 8 J .. of L11 (U-panel tiles), and those are final as soon as group J of the
+// factorisation is done.  So the diag CTA publishes group by group, straight from the registers that hold the finished rows / columns
+// (no staging through shared memory), and the panel CTAs trail the factorisation by about two groups instead of starting after all
+// 64 pivots: the serial chain of a block step loses most of the ~13 k cycles of a panel solve plus the publish / copy round trip.
+// The flag word of a block carries (epoch << 4) + groups published; 8 = the whole block.  The stores of group J are fenced and
+// flagged one group LATER (before the stores of group J + 1 are issued), when they have long left the SM: the fence costs nothing.
+constexpr int PUB_GROUPS = 8;
+__device__ __forceinline__ int pub_token(int epoch, int groups) { return (epoch << 4) + groups; }
+
+template <int J>
+__device__ __forceinline__ void publish_group(const double (&a)[4][8], const PivotLine& pl, double* __restrict__ img, int ty, int tx) {
+    constexpr int I = J >> 1;
+    // rows 8 J .. 8 J + 7 of U11 (scaled by the reciprocal pivot right of the diagonal): row p lives in register row I of the threads
+    // with ty == p & 15
+    const int pp = ty - ((8 * J) & 15);
+    if (pp >= 0 && pp < 8) {
+        const int p = 8 * J + pp;
+        const double rp = pl.rcp[p];
+#pragma unroll
+        for (int j = J; j < 8; ++j) {
+            const int c = tx + 8 * j;
+            if (c > p) img[p * TS + c] = a[I][j] * rp;
+            else if (c == p) img[p * TS + c] = a[I][j];
+        }
+        if (tx == pp) img[NB * TS + p] = rp;
+    }
+    // columns 8 J .. 8 J + 7 of L11: column 8 J + tx lives in register column J (unscaled multipliers) of the threads with that tx
+    {
+        const int p = 8 * J + tx;
+        const double rp = pl.rcp[p];
+#pragma unroll
+        for (int i = I; i < 4; ++i) {
+            const int r = ty + 16 * i;
+            if (r > p) img[r * TS + p] = a[i][J] * rp;
+        }
+    }
+}
+
+template <int J, int NT>
+__device__ __forceinline__ void factor_publish_step(double (&a)[4][8], PivotLine& pl, double* __restrict__ img, int* __restrict__ flag,
+                                                    int epoch, int ty, int tx) {
+    factor_group<J, NT>(a, pl, ty, tx);
+    if (J > 0) __threadfence();          // the stores of group J - 1, issued a whole group ago
+    panel_sync<NT>();                    // pl.rcp of this group complete; everybody's fence done
+    if (J > 0 && threadIdx.x == 0) st_release(flag, pub_token(epoch, J));
+    publish_group<J>(a, pl, img, ty, tx);
+}
+
+template <int NT = LU_THREADS, bool PIPE = false>
+__device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine& pl, double* __restrict__ img = nullptr,
+                                             int* __restrict__ flag = nullptr, int epoch = 0) {
     const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
     double a[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[i][j] = sC[(ty + 16 * i) * TS + tx + 8 * j];
+    if (PIPE) {
+        factor_publish_step<0, NT>(a, pl, img, flag, epoch, ty, tx);
+        factor_publish_step<1, NT>(a, pl, img, flag, epoch, ty, tx);
+        factor_publish_step<2, NT>(a, pl, img, flag, epoch, ty, tx);
+        factor_publish_step<3, NT>(a, pl, img, flag, epoch, ty, tx);
+        factor_publish_step<4, NT>(a, pl, img, flag, epoch, ty, tx);
+        factor_publish_step<5, NT>(a, pl, img, flag, epoch, ty, tx);
+        factor_publish_step<6, NT>(a, pl, img, flag, epoch, ty, tx);
+        factor_publish_step<7, NT>(a, pl, img, flag, epoch, ty, tx);
+        __threadfence();
+        panel_sync<NT>();
+        if (t == 0) st_release(flag, pub_token(epoch, PUB_GROUPS));
+    } else {
     factor_group<0, NT>(a, pl, ty, tx);
     factor_group<1, NT>(a, pl, ty, tx);
     factor_group<2, NT>(a, pl, ty, tx);
@@ -242,6 +306,7 @@ __device__ __forceinline__ void factor_block(double* __restrict__ sC, PivotLine&
     factor_group<6, NT>(a, pl, ty, tx);
     factor_group<7, NT>(a, pl, ty, tx);
     panel_sync<NT>();      // pl.rcp complete
+    }
     // registers hold U on and above the diagonal and the unscaled multipliers below it: L(r, c) = a(r, c) / U(c, c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -302,6 +367,52 @@ __device__ __forceinline__ void panel_solve(double (&a)[RI][8], const double* __
     panel_group<5, TR, RI>(a, sW, dinv, tx, lane);
     panel_group<6, TR, RI>(a, sW, dinv, tx, lane);
     panel_group<7, TR, RI>(a, sW, dinv, tx, lane);
+}
+
+// The consumer side of the pipelined publication: group J of the solve waits until group J of the factors is published, fetches just
+// that part of the image (8 rows of U11 and their reciprocal pivots for an L-panel tile or the inverse, 8 columns of L11 for a U-panel
+// tile) into the shared-memory image at sW, and runs.  Threads 0 .. 127 of the CTA, barrier panel_sync<NT>().
+template <int J, bool TR, int RI, int NT>
+__device__ __forceinline__ void panel_group_piped(double (&a)[RI][8], double* __restrict__ sW, double* __restrict__ dinv,
+                                                  const double* __restrict__ img, const int* __restrict__ flag, int epoch, int tx, int lane) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        const int want = pub_token(epoch, J + 1);
+        while (ld_acquire(flag) < want) __nanosleep(20);
+    }
+    panel_sync<NT>();
+    if (TR) {       // columns 8 J .. 8 J + 7 of the image, all 64 rows: thread t fetches 4 doubles of row t / 2
+        const int r = t >> 1, c = 8 * J + (t & 1) * 4;
+        const double2* g = reinterpret_cast<const double2*>(img + r * TS + c);
+        const double2 v0 = __ldcg(g), v1 = __ldcg(g + 1);
+        double2* d = reinterpret_cast<double2*>(sW + r * TS + c);
+        d[0] = v0;
+        d[1] = v1;
+    } else {        // rows 8 J .. 8 J + 7, all 64 columns: thread t fetches 4 doubles of row 8 J + t / 16
+        const int r = 8 * J + (t >> 4), c = (t & 15) * 4;
+        const double2* g = reinterpret_cast<const double2*>(img + r * TS + c);
+        const double2 v0 = __ldcg(g), v1 = __ldcg(g + 1);
+        double2* d = reinterpret_cast<double2*>(sW + r * TS + c);
+        d[0] = v0;
+        d[1] = v1;
+        if (t < 8) dinv[8 * J + t] = __ldcg(img + NB * TS + 8 * J + t);
+    }
+    panel_sync<NT>();
+    panel_group<J, TR, RI>(a, sW, dinv, tx, lane);
+}
+
+template <bool TR, int RI, int NT>
+__device__ __forceinline__ void panel_solve_piped(double (&a)[RI][8], double* __restrict__ sW, double* __restrict__ dinv,
+                                                  const double* __restrict__ img, const int* __restrict__ flag, int epoch) {
+    const int tx = threadIdx.x & 7, lane = threadIdx.x & 31;
+    panel_group_piped<0, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
+    panel_group_piped<1, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
+    panel_group_piped<2, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
+    panel_group_piped<3, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
+    panel_group_piped<4, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
+    panel_group_piped<5, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
+    panel_group_piped<6, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
+    panel_group_piped<7, TR, RI, NT>(a, sW, dinv, img, flag, epoch, tx, lane);
 }
 
 // y = L^-1 b for the unit-lower factor held row-major in sC; warp 0 only, lane l keeps b[l] and b[l + 32]

@@ -63,6 +63,21 @@ def main():
         out[label] = {"seconds_per_solve": float(np.median(times)), "solves": solves, "vji_flow_seconds": flow["s"],
                       "CL": tot.get("CL"), "CD": tot.get("CD"), "Cm": tot.get("Cm")}
 
+    if "--sweep" in sys.argv:
+        # BASELINE.json configs[2]: the reference's serial idiom set_aircraft_state -> solve_forces (scene.py:1535-1598) over a list of
+        # flight states; as shipped (1 BLAS thread; the 180-point systems do not thread anyway)
+        with open(sys.argv[sys.argv.index("--sweep") + 1]) as fh:
+            states = json.load(fh)
+        name = list(scene._airplanes.keys())[0]
+        t = time.perf_counter()
+        cl = []
+        for st in states:
+            scene.set_aircraft_state(state=dict(st), aircraft=name)
+            cl.append(scene.solve_forces()[name]["total"]["CL"])
+        dt = time.perf_counter() - t
+        out["sweep"] = {"cases": len(states), "seconds": dt, "cases_per_second": len(states) / dt, "CL_first_last": [cl[0], cl[-1]]}
+        print(json.dumps(out))
+        return
     run("as_shipped_1_blas_thread")
     if all_cores:
         try:
