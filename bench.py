@@ -541,6 +541,14 @@ def run_ours_c3(args):
     e1.record()
     barrier()
     res_ms = e0.elapsed_time(e1)
+    # per-phase device times of one sweep of this rank's shard (instrumented pass: the phase timers synchronise)
+    import ctypes
+    _native.check(lib.lls_set_timing(bdev.handle, 1))
+    bdev.solve(sc._solver_type, sc._solver_convergence, sc._solver_relaxation, sc._max_solver_iterations, sc._impingement_threshold)
+    ms6 = (ctypes.c_double * 6)()
+    _native.check(lib.lls_get_timings(bdev.handle, ms6))
+    _native.check(lib.lls_set_timing(bdev.handle, 0))
+    phase = dict(zip(("influence", "assemble", "lu", "trisolve", "residual", "integrate"), list(ms6)))
     if world > 1:
         t = torch.tensor([dev_ms, wall_ms, res_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -579,7 +587,7 @@ def run_ours_c3(args):
         "roofline": {"kernel": "lu_small_case_kernel: one CTA factors and solves one case (3 block rows), DMMA trailing updates",
                      "bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
                      "note": "latency-bound small systems; see DESIGN.md section 6.1"},
-        "parity": parity, "cpu_baseline": None,
+        "phase_ms": phase, "parity": parity, "cpu_baseline": None,
     }
     print(json.dumps(line))
     if world > 1:
