@@ -665,11 +665,15 @@ __device__ __forceinline__ void dist_arrive(const DistPeers& pr, int rem, int Gn
     }
 }
 
-template <bool FIRST>
+// PASSES = 2 (rank-128 visit, as in the single-GPU kernel): the tiles take the updates of panels k AND k + 1 in one visit -- half the
+// traffic on C, twice the tensor work per tile visit -- and the roles factor panel k + 2; the tiles of block row / column k + 1 were
+// brought up to date, and panel k + 1 factored and exchanged, by a THIN launch just before (a PASSES = 1 launch whose grid stops
+// after the panel roles: `thin`).  Used while the bulk of a launch outweighs the exposed chain of the thin launch.
+template <bool FIRST, int PASSES = 1>
 __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __restrict__ Mloc, int ld, int k, int nblk, int lb0, int nloc,
                                                                      double* __restrict__ rhs, DistPeers pr, int Gn,
                                                                      double* __restrict__ uinv, double* __restrict__ scalars,
-                                                                     int* __restrict__ status) {
+                                                                     int* __restrict__ status, int thin) {
     extern __shared__ __align__(16) double sm[];
     double* sA = sm;
     double* sB = sm + NB * TS;
@@ -678,8 +682,9 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
     __shared__ double yk[NB];
     const int t = threadIdx.x, b = blockIdx.x;
     const int P = pr.P, rank = pr.rank;
-    const int base = k + 1, rem = nblk - base;          // trailing matrix: block rows / columns base .. nblk - 1
-    const int Gc = Gn - 1;                              // global index of panel k (not FIRST)
+    static_assert(!(FIRST && PASSES != 1), "the first launch has nothing to update");
+    const int base = k + PASSES, rem = nblk - base;     // trailing matrix handled here: block rows / columns base .. nblk - 1
+    const int Gc = Gn - PASSES;                         // global index of panel k (not FIRST); panel k + 1 is Gc + 1
     if (b == 0 && t < P) st_release_sys(pr.progress[t] + rank, FIRST ? Gn : Gc);    // every global step below this one is consumed here
     const bool own = (base % P == rank);                // this rank owns block row base: its local block lb0
     enum { DIAG, UROW, LCOL, OTHER } role;
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
         else if (b < nd + nu + rows_below) { role = LCOL; lb = lb0 + nd + (b - nd - nu); bj = base; }
         else {
             const int o = b - nd - nu - rows_below;
-            if (rem <= 1 || o >= rows_below * (rem - 1)) return;       // nothing left for this rank: the launch only reported progress
+            if (thin || rem <= 1 || o >= rows_below * (rem - 1)) return;       // nothing (left) for this rank: the launch only reported progress
             role = OTHER; lb = lb0 + nd + o / (rem - 1); bj = base + 1 + o % (rem - 1);
         }
     }
@@ -712,12 +717,25 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
                 dist_wait(pr.flags[rank] + (Gc % DIST_RING), [want](int v) { return v == want; }, pr, status, b == 0 ? pr.stats : nullptr);
             }
             __syncthreads();
-            load_tile_async(sB, pr.slots[rank] + (size_t)(Gc % pr.S) * pr.slot_doubles + DIST_HDR + (size_t)(bj - base) * NB * NB, NB);   // U[k,j]
+            load_tile_async(sB, pr.slots[rank] + (size_t)(Gc % pr.S) * pr.slot_doubles + DIST_HDR + (size_t)(bj - base + PASSES - 1) * NB * NB, NB);   // U[k,j]
             async_wait_all();
             c_negate(acc, cn);
         }
         __syncthreads();
         mma_tile(sA, sB, acc);
+        if (PASSES == 2) {
+            __syncthreads();
+            load_tile_async(sA, Mloc + (size_t)lb * NB * ld + (size_t)(k + 1) * NB, ld);                             // L[i,k+1]
+            if (t == 0) {
+                const int want = Gc + 2;
+                dist_wait(pr.flags[rank] + ((Gc + 1) % DIST_RING), [want](int v) { return v == want; }, pr, status, b == 0 ? pr.stats : nullptr);
+            }
+            __syncthreads();
+            load_tile_async(sB, pr.slots[rank] + (size_t)((Gc + 1) % pr.S) * pr.slot_doubles + DIST_HDR + (size_t)(bj - base) * NB * NB, NB);   // U[k+1,j]
+            async_wait_all();
+            __syncthreads();
+            mma_tile(sA, sB, acc);
+        }
         if (role == OTHER) {
             acc_io<false>(acc, gC, ld);
             return;
@@ -943,8 +961,9 @@ int dist_comm_create(Scene* s, int slots, unsigned char* handle64) {
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_owner_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_panel_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
-        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+        LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
         attr = true;
     }
     return LLS_OK;
@@ -1023,25 +1042,48 @@ int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st) 
         const char* env = getenv("LLS_PARTITIONED_FUSED_STEPS");
         fused_steps = (env != nullptr && env[0] == '0') ? 0 : 1;
     }
+    static int pair_min_rem = -1;       // LLS_PARTITIONED_PAIR_MIN_REM: rank-128 visits while the trailing matrix has at least this many block rows (0 = never); default 64 sqrt(P)
+    if (pair_min_rem < 0) {
+        const char* env = getenv("LLS_PARTITIONED_PAIR_MIN_REM");
+        pair_min_rem = env != nullptr ? atoi(env) : -2;
+    }
+    int pair_min = pair_min_rem;
+    if (pair_min == -2) { pair_min = 64; while ((long long)pair_min * pair_min < 4096LL * P) pair_min += 8; }      // ~ 64 sqrt(P)
     if (fused_steps) {
-        for (int k = -1; k + 1 < nblk; ++k) {
-            const int base = k + 1, rem = nblk - base;
+        // launch(k, passes, thin): tiles with block rows / columns >= k + passes take panels k .. k + passes - 1, roles factor panel k + passes
+        auto launch = [&](int k, int passes, int thin) {
+            const int base = k + passes, rem = nblk - base;
             int lb0 = (base - rank + P - 1) / P;           // first local block whose global index lb * P + rank is >= base
             if (lb0 < 0) lb0 = 0;
             const int nloc = s->n_loc_blocks - lb0 > 0 ? s->n_loc_blocks - lb0 : 0;
             const bool own = (base % P == rank);
             const int nd = own ? 1 : 0, below = nloc - nd;
-            long long grid = nd + (own ? rem - 1 : 0) + below + (k >= 0 ? (long long)below * (rem - 1) : 0);
+            long long grid = nd + (own ? rem - 1 : 0) + below + ((k >= 0 && !thin) ? (long long)below * (rem - 1) : 0);
             if (grid < 1) grid = 1;
             const int Gn = (int)(G0 + base);
             if (k < 0) {
-                lu_dist_step_kernel<true><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
-                                                                                             s->scalars, s->status);
+                lu_dist_step_kernel<true, 1><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
+                                                                                                s->scalars, s->status, thin);
+            } else if (passes == 1) {
+                lu_dist_step_kernel<false, 1><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
+                                                                                                 s->scalars, s->status, thin);
             } else {
-                lu_dist_step_kernel<false><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
-                                                                                              s->scalars, s->status);
+                lu_dist_step_kernel<false, 2><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
+                                                                                                 s->scalars, s->status, thin);
             }
             count_launch();
+        };
+        launch(-1, 1, 0);                                  // panel 0
+        for (int k = 0; k + 1 < nblk;) {
+            const int rem = nblk - 1 - k;                  // block rows of the trailing matrix after step k
+            if (pair_min > 0 && rem >= pair_min && k + 2 < nblk) {
+                launch(k, 1, 1);                           // thin: block row / column k + 1 take panel k, panel k + 1 factored and exchanged
+                launch(k, 2, 0);                           // the rest takes panels k and k + 1 in one visit, panel k + 2 on the way
+                k += 2;
+            } else {
+                launch(k, 1, 0);
+                k += 1;
+            }
         }
     } else {
     if (0 % P == rank) owner(0);

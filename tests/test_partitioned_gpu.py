@@ -25,8 +25,10 @@ def _parse(stdout, fixtures=FIXTURES):
     return rows
 
 
-def _run(world, fixtures, p2p, port):
+def _run(world, fixtures, p2p, port, pair_min_rem=None):
     env = dict(os.environ, LLS_PARTITIONED_P2P="1" if p2p else "0")
+    if pair_min_rem is not None:      # rank-128 paired visits from this many block rows on (the default threshold is far above the fixtures)
+        env["LLS_PARTITIONED_PAIR_MIN_REM"] = str(pair_min_rem)
     script = os.path.join(ROOT, "scripts", "dist_check.py")
     if world == 1:
         cmd = [sys.executable, script] + fixtures
@@ -43,6 +45,11 @@ def _run(world, fixtures, p2p, port):
 @pytest.mark.parametrize("p2p", [True, False])
 def test_partitioned_world_size_1(p2p):
     _run(1, FIXTURES, p2p, 0)
+
+
+def test_partitioned_paired_visits_world_size_1():
+    """Thin launch + rank-128 visit for every pair of block steps (threshold forced down to 2 block rows), incl. N = 4000."""
+    _run(1, FIXTURES + ["c2_traditional_n4000"], True, 0, pair_min_rem=2)
 
 
 def _visible_gpus():
@@ -62,6 +69,7 @@ def test_partitioned_multi_gpu(p2p):
         rows = _run(world, FIXTURES + (["c2_traditional_n4000"] if world == 2 else []), p2p, 29533 + world)
         if p2p:
             assert all(r["exchange_stats"]["block_steps"] > 0 for r in rows)
+            _run(world, FIXTURES + (["c2_traditional_n4000"] if world == 2 else []), True, 29543 + world, pair_min_rem=2)     # paired visits
 
 
 def test_partitioned_world_sizes_agree_on_a_lattice_swarm():
