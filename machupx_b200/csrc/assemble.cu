@@ -109,8 +109,11 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int flags, const double* __restrict__ tab,
+// THREADS threads share a row; ROWS rows per CTA.  ROWS > 1 needs THREADS == 32 (one warp per row, reduction by shuffles only): the
+// shape for the small scenes of large batches, where a row is shorter than a CTA and the scalar tail of the row (section lift,
+// Jacobian row vectors) is what there is to hide.
+template <int THREADS, int ROWS = 1>
+__global__ void __launch_bounds__(THREADS * ROWS) residual_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                            const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                            const double* __restrict__ V, double* __restrict__ W,
                                                            double* __restrict__ out, double* __restrict__ partial, int vel_only,
@@ -121,7 +124,9 @@ __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int fl
     W = case_work_ptr(W, cs.work);
     out = case_ptr(out, cs.out);
     partial = case_work_ptr(partial, cs.work);
-    const int li = blockIdx.x;                        // row of this rank's V
+    static_assert(ROWS == 1 || THREADS == 32, "several rows per CTA: one warp per row");
+    const int tid = (ROWS == 1) ? threadIdx.x : (threadIdx.x & 31);
+    const int li = (ROWS == 1) ? blockIdx.x : blockIdx.x * ROWS + (threadIdx.x >> 5);    // row of this rank's V
     const int i = global_row(cs, li);
     if (i >= n) return;
     const double* gamma = out + (size_t)LLS_O_GAMMA * ld;
@@ -130,28 +135,32 @@ __global__ void __launch_bounds__(THREADS) residual_kernel(int n, int ld, int fl
     const double2* v2 = reinterpret_cast<const double2*>(V + (size_t)li * 3 * ld + 2 * (size_t)ld);
     const double2* g2 = reinterpret_cast<const double2*>(gamma);
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int j = threadIdx.x; j < ld / 2; j += THREADS) {
+    for (int j = tid; j < ld / 2; j += THREADS) {
         const double2 g = g2[j], a = v0[j], b = v1[j], c = v2[j];
         sx = fma(a.x, g.x, fma(a.y, g.y, sx));
         sy = fma(b.x, g.x, fma(b.y, g.y, sy));
         sz = fma(c.x, g.x, fma(c.y, g.y, sz));
     }
-    __shared__ double red[3][THREADS / 32];
     sx = warp_sum(sx);
     sy = warp_sum(sy);
     sz = warp_sum(sz);
-    if ((threadIdx.x & 31) == 0) {
-        red[0][threadIdx.x >> 5] = sx;
-        red[1][threadIdx.x >> 5] = sy;
-        red[2][threadIdx.x >> 5] = sz;
-    }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    sx = sy = sz = 0.0;
-    for (int w = 0; w < THREADS / 32; ++w) {
-        sx += red[0][w];
-        sy += red[1][w];
-        sz += red[2][w];
+    if (THREADS > 32) {
+        __shared__ double red[3][THREADS / 32];
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = sx;
+            red[1][threadIdx.x >> 5] = sy;
+            red[2][threadIdx.x >> 5] = sz;
+        }
+        __syncthreads();
+        if (threadIdx.x != 0) return;
+        sx = sy = sz = 0.0;
+        for (int w = 0; w < THREADS / 32; ++w) {
+            sx += red[0][w];
+            sy += red[1][w];
+            sz += red[2][w];
+        }
+    } else if (tid != 0) {
+        return;
     }
     const Vec3 vi = ld3(W, ld, W_VIR, i) + Vec3{sx, sy, sz};                       // scene.py:728
     if (vel_only) {  // integration pre-pass of a linear solve: only v_i is refreshed (scene.py:943)
@@ -261,8 +270,15 @@ int launch_assemble_linear(Scene* s, cudaStream_t st) {
 }
 
 int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked) {
-    residual_kernel<128><<<dim3(s->cs.P == 1 ? s->n : s->n_loc_blocks * 64, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
-                                                                  vel_only, s->status, strides(s, masked));
+    const int rows = s->cs.P == 1 ? s->n : s->n_loc_blocks * 64;
+    if (s->ld <= 512 && s->ncases > 1) {
+        // small scenes in large batches: one warp per row, 8 rows per CTA
+        residual_kernel<32, 8><<<dim3((rows + 7) / 8, 1, s->ncases), 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out,
+                                                                                s->partial, vel_only, s->status, strides(s, masked));
+    } else {
+        residual_kernel<128><<<dim3(rows, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
+                                                                      vel_only, s->status, strides(s, masked));
+    }
     count_launch();
     if (!vel_only) {
         sum_kernel<<<dim3(1, 1, s->ncases), 256, 0, st>>>(s->n, s->partial, s->scalars, 0, strides(s, masked));

@@ -710,13 +710,10 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
         double acc[4][4][2];
         {
             double2 cn[4][4];
+            // No flag is polled here: the L-panel CTAs of the launch that factored panel k did not exit before "panel k complete" had
+            // arrived in this rank's mailbox (see the end of the LCOL role), so the kernel boundary already orders these loads after it
             c_fetch(cn, gC, ld);
             load_tile_async(sA, Mloc + (size_t)lb * NB * ld + (size_t)k * NB, ld);                                   // L[i,k]
-            if (t == 0) {
-                const int want = Gc + 1;
-                dist_wait(pr.flags[rank] + (Gc % DIST_RING), [want](int v) { return v == want; }, pr, status, b == 0 ? pr.stats : nullptr);
-            }
-            __syncthreads();
             load_tile_async(sB, pr.slots[rank] + (size_t)(Gc % pr.S) * pr.slot_doubles + DIST_HDR + (size_t)(bj - base + PASSES - 1) * NB * NB, NB);   // U[k,j]
             async_wait_all();
             c_negate(acc, cn);
@@ -726,11 +723,6 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
         if (PASSES == 2) {
             __syncthreads();
             load_tile_async(sA, Mloc + (size_t)lb * NB * ld + (size_t)(k + 1) * NB, ld);                             // L[i,k+1]
-            if (t == 0) {
-                const int want = Gc + 2;
-                dist_wait(pr.flags[rank] + ((Gc + 1) % DIST_RING), [want](int v) { return v == want; }, pr, status, b == 0 ? pr.stats : nullptr);
-            }
-            __syncthreads();
             load_tile_async(sB, pr.slots[rank] + (size_t)((Gc + 1) % pr.S) * pr.slot_doubles + DIST_HDR + (size_t)(bj - base) * NB * NB, NB);   // U[k+1,j]
             async_wait_all();
             __syncthreads();
@@ -859,11 +851,20 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
         store_tile(gC, ld, sC);
         if (role == UROW) {
             store_tile_all(pr, next_off + DIST_HDR + (size_t)(bj - base - 1) * NB * NB, sC);      // U[k+1,j] into every rank's slot
-        } else if (t < NB) {
-            double sdot = 0.0;
+        } else {
+            if (t < NB) {
+                double sdot = 0.0;
 #pragma unroll 8
-            for (int q = 0; q < NB; ++q) sdot = fma(sC[t * TS + q], yk[q], sdot);
-            rhs[(size_t)bi * NB + t] -= sdot;
+                for (int q = 0; q < NB; ++q) sdot = fma(sC[t * TS + q], yk[q], sdot);
+                rhs[(size_t)bi * NB + t] -= sdot;
+            }
+            // This CTA's work is done; it stays until the WHOLE of panel k + 1 (every U tile) has landed in this rank's mailbox, so
+            // that the next launch can read it without polling.  Normally the flag is long set (the owner's U-row CTAs run beside
+            // the L-panel CTAs); what is waited here is the exposed part of the exchange, accounted in stats[0].
+            if (t == 0) {
+                const int want = Gn + 1;
+                dist_wait(pr.flags[rank] + (Gn % DIST_RING), [want](int v) { return v == want; }, pr, status, lb == lb0 + (own ? 1 : 0) ? pr.stats : nullptr);
+            }
         }
     }
     if (role == UROW) {

@@ -25,7 +25,7 @@ for r in rows:
 allus = sum(v[1] for v in tot.values())
 with open(os.path.join(P, tag + "_launch_shares_c2.csv"), "w") as fh:
     fh.write("# ncu launch list, one C2 solve (N=4000): python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n")
-    fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:<our kernels> -s 3500 -c 900 (cold-cache, serialised: compare SHARES)\n")
+    fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 3300 -c 1100 (r1: -s 3500 -c 900; about 1.3 solves; cold-cache, serialised: compare SHARES)\n")
     fh.write("kernel,launches,total_us,share\n")
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
         fh.write("%s,%d,%.1f,%.4f\n" % (k, v[0], v[1], v[1] / allus))
@@ -56,7 +56,13 @@ def summarise(rep, out, header):
 summarise(pre + "_lu.ncu-rep", tag + "_lu_step_full.txt",
           "# ncu --set full --clock-control none --import-source on -k regex:lu_step_kernel -s 198 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline  (C2, N=4000; block step 8 of the 4th factorisation)")
 summarise(pre + "_influence.ncu-rep", tag + "_influence_full.txt",
-          "# ncu --set full --clock-control none --import-source on -k regex:influence_kernel -s 2 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline  (C2, N=4000)")
+          "# ncu --set full --clock-control none --import-source on -k regex:influence_kernel -s 4 -c 2 (r1: -s 2 -c 1) python bench.py --steps 1 --warmup 3 --no-cpu-baseline  (C2, N=4000; r2: <2> = plain tiles, <1> = blend tiles of the same grid)")
+if os.path.exists(os.path.join(G, pre + "_dist.ncu-rep")):
+    summarise(pre + "_dist.ncu-rep", tag + "_lu_dist_step_full.txt",
+              "# ncu --set full --clock-control none --import-source on -k regex:lu_dist_step_kernel -s 72 -c 1 python scripts/dist_check.py c2_traditional_n4000  (row-partitioned LU, world size 1, N=4000; a bulk block step of 2916 tiles: compare with the lu_step_kernel launch of the same size)")
+if os.path.exists(os.path.join(G, pre + "_small.ncu-rep")):
+    summarise(pre + "_small.ncu-rep", tag + "_lu_small_case_full.txt",
+              "# ncu --set full --clock-control none --import-source on -k regex:lu_small_case_kernel -s 30 -c 1 python bench.py --workload c3 --steps 1 --warmup 3  (4,096 cases of 3 block rows, one CTA per case)")
 print(open(os.path.join(P, tag + "_launch_shares_c2.csv")).read())
 print(open(os.path.join(P, tag + "_lu_step_full.txt")).read())
 print(open(os.path.join(P, tag + "_influence_full.txt")).read())
