@@ -455,8 +455,12 @@ def run_ours_swarm(args):
                                     "(Newton iterations + 1) x 2/3 N^3 flop / LU phase time / n_gpus",
                      "flops_per_solve": lu_flops, "ms_per_solve": tm["lu"], "factorisations_per_solve": n_fact},
         "phase_ms": tm,
-        "exchange": {"path": ("peer-memory mailboxes (owner kernel stores panels into every GPU over NVLink, flags, one-panel look-ahead)"
+        "exchange": {"path": (("peer-memory mailboxes: the owner's role CTAs store the next panel into every GPU's mailbox from inside the step "
+                               "kernel, " + ("ONE multicast store per element replicated by the NVSwitch (NVLS)" if getattr(dev, "multicast", False)
+                                             else "unicast P2P stores to every peer over NVLink") + ", arrival flags, no collective call")
                               if (partitioned and dev.fused_exchange) else ("NCCL broadcast per block step" if partitioned else "none (one GPU)")),
+                     "multicast": bool(getattr(dev, "multicast", False)) if partitioned else None,
+                     "fallback_reason": getattr(dev, "exchange_error", None) if partitioned else None,
                      "per_rank_wait_ms_per_step": {"panel_wait, slot_wait": waits},
                      "note": "panel_wait = time block 0 of the L-panel kernels spent waiting for the owner's panel to land (exposed "
                              "exchange + owner-panel latency); slot_wait = time owner kernels waited for a free mailbox slot"},

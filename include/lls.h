@@ -247,8 +247,17 @@ int lls_dist_back(lls_scene* h, int k, void* stream);
  *                           A peer that never arrives raises LLS_STATUS_COMM after 30 s instead of hanging.
  *   lls_dist_comm_stats   : out4 = {ms the panel kernels waited for panels, ms the owner kernels waited for free slots,
  *                           global block steps so far, back substitutions so far}; resets the two timers.
- *   lls_dist_comm_destroy : closes the peers' mailboxes and frees the own one (also done by lls_destroy). */
+ *   lls_dist_comm_destroy : closes the peers' mailboxes and frees the own one (also done by lls_destroy).
+ *   lls_dist_comm_bytes / lls_dist_comm_attach : the alternative to create + connect when the HOST owns symmetric memory (e.g.
+ *                           torch.distributed._symmetric_memory): d_mailboxes = world device pointers, the mailbox of every rank as
+ *                           mapped into this process (lls_dist_comm_bytes bytes each, zero-filled), d_multicast = the multicast
+ *                           (NVLS) mapping of all of them or NULL.  With a multicast mapping every panel store of an owner kernel is
+ *                           ONE store replicated by the NVSwitch into all mailboxes: the owner's link carries a panel once instead of
+ *                           world - 1 times.  lls_dist_comm_multicast returns 1 if such a mapping is attached. */
 int lls_dist_comm_create(lls_scene* h, int slots, unsigned char* ipc_handle_out64);
+int lls_dist_comm_bytes(lls_scene* h, int slots, size_t* bytes);
+int lls_dist_comm_attach(lls_scene* h, int slots, void* const* d_mailboxes, void* d_multicast);
+int lls_dist_comm_multicast(lls_scene* h);
 int lls_dist_comm_connect(lls_scene* h, const unsigned char* all_handles);
 int lls_dist_lu_solve(lls_scene* h, void* stream);
 int lls_dist_comm_stats(lls_scene* h, double* out4, void* stream);

@@ -46,6 +46,9 @@ SIGNATURES = {
     "lls_dist_back": (_i, [_vp, _i, _vp]),
     "lls_dist_comm_create": (_i, [_vp, _i, _vp]),
     "lls_dist_comm_connect": (_i, [_vp, _vp]),
+    "lls_dist_comm_bytes": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_size_t)]),
+    "lls_dist_comm_attach": (_i, [_vp, _i, ctypes.POINTER(_vp), _vp]),
+    "lls_dist_comm_multicast": (_i, [_vp]),
     "lls_dist_lu_solve": (_i, [_vp, _vp]),
     "lls_dist_comm_stats": (_i, [_vp, _pd, _vp]),
     "lls_dist_comm_destroy": (_i, [_vp]),

@@ -430,6 +430,22 @@ extern "C" int lls_dist_comm_create(lls_scene* h, int slots, unsigned char* ipc_
     return dist_comm_create(h, slots, ipc_handle_out64);
 }
 
+extern "C" int lls_dist_comm_bytes(lls_scene* h, int slots, size_t* bytes) {
+    LLS_CHECK_BOUND(h);
+    LLS_REQUIRE(bytes != nullptr, LLS_ERR_ARG, "lls_dist_comm_bytes: null output");
+    *bytes = dist_comm_bytes(h, slots);
+    return LLS_OK;
+}
+
+extern "C" int lls_dist_comm_attach(lls_scene* h, int slots, void* const* d_mailboxes, void* d_multicast) {
+    LLS_CHECK_BOUND(h);
+    LLS_CHECK_PART(h);
+    LLS_REQUIRE(d_mailboxes != nullptr, LLS_ERR_ARG, "lls_dist_comm_attach: null mailbox list");
+    return dist_comm_attach(h, slots, d_mailboxes, d_multicast);
+}
+
+extern "C" int lls_dist_comm_multicast(lls_scene* h) { return (h != nullptr) ? dist_comm_multicast(h) : 0; }
+
 extern "C" int lls_dist_comm_connect(lls_scene* h, const unsigned char* all_handles) {
     LLS_CHECK_BOUND(h);
     LLS_REQUIRE(all_handles != nullptr || h->cs.P == 1, LLS_ERR_ARG, "lls_dist_comm_connect: null handles");

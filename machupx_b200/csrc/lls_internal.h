@@ -146,6 +146,9 @@ int lu_dist_back(Scene* s, int k, const double* y, double* x, cudaStream_t st);
 // row-partitioned LU with the exchange inside the kernels (mailboxes in peer memory, CUDA IPC between the processes)
 int dist_comm_create(Scene* s, int slots, unsigned char* handle64);
 int dist_comm_connect(Scene* s, const unsigned char* handles);
+size_t dist_comm_bytes(const Scene* s, int slots);
+int dist_comm_attach(Scene* s, int slots, void* const* bases, void* mc);
+int dist_comm_multicast(const Scene* s);
 int dist_comm_destroy(Scene* s);
 int dist_comm_stats(Scene* s, double* out4, cudaStream_t st);
 int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st);

@@ -327,6 +327,8 @@ struct DistPeers {
     int* progress[DIST_MAX_P];
     double* xbuf[DIST_MAX_P];
     int* xflags[DIST_MAX_P];
+    double* mc_slots;         // the slots / the solution of EVERY rank at once: multicast mapping of the mailboxes through the NVSwitch
+    double* mc_xbuf;          // (NVLS; null without it): one store lands in all mailboxes, the owner's link carries a panel once, not P - 1 times
     int* own;                 // local: ring of intra-kernel flags of the owner kernel (diag tile published to the U-row CTAs)
     int* counter;             // local: CTAs of the owner kernel that have finished their stores
     int* abort;               // local: set once a deadline has passed: every later wait returns at once
@@ -337,6 +339,8 @@ struct DistPeers {
 
 struct DistComm {
     char* base[DIST_MAX_P] = {nullptr};     // mailbox of every rank as mapped into this process ([rank] = the one we own)
+    char* mc = nullptr;                     // multicast mapping of all mailboxes (external symmetric memory only)
+    bool external = false;                  // the mailboxes belong to the caller (lls_dist_comm_attach): nothing to free or close
     bool opened[DIST_MAX_P] = {false};
     size_t bytes = 0;
     DistPeers peers;
@@ -380,9 +384,53 @@ __device__ __forceinline__ bool dist_wait(const int* p, Pred ok, const DistPeers
     return true;
 }
 
+// 16 bytes to a multicast address: the switch replicates the store into every rank's memory
+__device__ __forceinline__ void mc_store2(double* p, double2 v) {
+    const float4 b = *reinterpret_cast<const float4*>(&v);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+__device__ __forceinline__ void mc_store1(double* p, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 // 64 x 64 tile in shared memory (row stride TS) -> the same place in every rank's slot (row stride NB)
 __device__ __forceinline__ void store_tile_all(const DistPeers& pr, size_t offset, const double* __restrict__ s) {
+    if (pr.mc_slots != nullptr) {
+        const int t = threadIdx.x, c2 = t & 31, r0 = t >> 5;
+        double* g = pr.mc_slots + offset;
+#pragma unroll 4
+        for (int r = r0; r < NB; r += 4) mc_store2(g + (size_t)r * NB + 2 * c2, *reinterpret_cast<const double2*>(s + r * TS + 2 * c2));
+        return;
+    }
     for (int q = 0; q < pr.P; ++q) store_tile(pr.slots[q] + offset, NB, s);
+}
+// the image of a factored diagonal block (shared memory, IMG2 double2) and its reciprocal pivots into every OTHER rank's slot
+__device__ __forceinline__ void store_image_all(const DistPeers& pr, size_t slot_off, const double* __restrict__ sA, const double* __restrict__ dinv) {
+    constexpr int IMG2 = NB * TS / 2;
+    const int t = threadIdx.x;
+    const double2* s0 = reinterpret_cast<const double2*>(sA);
+    if (pr.mc_slots != nullptr) {
+        double* g = pr.mc_slots + slot_off;
+#pragma unroll
+        for (int e = t; e < IMG2; e += LU_THREADS) mc_store2(g + 2 * e, s0[e]);
+        if (t < NB) mc_store1(g + NB * TS + t, dinv[t]);
+        return;
+    }
+    for (int q = 0; q < pr.P; ++q) {
+        if (q == pr.rank) continue;
+        double2* g0 = reinterpret_cast<double2*>(pr.slots[q] + slot_off);
+#pragma unroll
+        for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
+        if (t < NB) pr.slots[q][slot_off + NB * TS + t] = dinv[t];
+    }
+}
+// one double of the step buffer (y_k) / of the solution into every rank's mailbox
+__device__ __forceinline__ void store_slot_all(const DistPeers& pr, size_t off, double v) {
+    if (pr.mc_slots != nullptr) { mc_store1(pr.mc_slots + off, v); return; }
+    for (int q = 0; q < pr.P; ++q) pr.slots[q][off] = v;
+}
+__device__ __forceinline__ void store_x_all(const DistPeers& pr, size_t off, double v) {
+    if (pr.mc_xbuf != nullptr) { mc_store1(pr.mc_xbuf + off, v); return; }
+    for (int q = 0; q < pr.P; ++q) pr.xbuf[q][off] = v;
 }
 
 __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_owner_p2p_kernel(double* __restrict__ Mloc, int ld, int k, int lbk, int ncols,
@@ -431,24 +479,15 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_owner_p2p_kernel(double
         __threadfence();
         __syncthreads();
         if (t == 0) st_release(pr.own + (G % DIST_RING), G + 1);
-        for (int q = 0; q < pr.P; ++q) {
-            if (q == pr.rank) continue;
-            double2* g0 = reinterpret_cast<double2*>(pr.slots[q] + slot_off);
-            const double2* s0 = reinterpret_cast<const double2*>(sA);
-#pragma unroll
-            for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
-            if (t < NB) pr.slots[q][slot_off + NB * TS + t] = dinv[t];
-        }
+        store_image_all(pr, slot_off, sA, dinv);
         store_tile(gC, ld, sC);
         pivot_guard<LU_THREADS>(sC, pl, k < pr.P, k + pr.P >= ld / NB, scalars, status);
         if (rhs != nullptr && t < 32) {
             forward_rhs_warp(sC, rhs + (size_t)k * NB);
             __syncwarp();
             const double y0 = rhs[(size_t)k * NB + t], y1 = rhs[(size_t)k * NB + 32 + t];
-            for (int q = 0; q < pr.P; ++q) {
-                pr.slots[q][slot_off + PUB_DOUBLES + t] = y0;
-                pr.slots[q][slot_off + PUB_DOUBLES + 32 + t] = y1;
-            }
+            store_slot_all(pr, slot_off + PUB_DOUBLES + t, y0);
+            store_slot_all(pr, slot_off + PUB_DOUBLES + 32 + t, y1);
         }
     } else {
         if (t == 0) {
@@ -630,7 +669,7 @@ __global__ void __launch_bounds__(NB) lu_dist_backsolve_p2p_kernel(const double*
             s3 = fma(ui[c + 1].y, b.y, s3);
         }
         const double xv = (s0 + s1) + (s2 + s3);
-        for (int q = 0; q < pr.P; ++q) pr.xbuf[q][(size_t)bi * NB + t] = xv;
+        store_x_all(pr, (size_t)bi * NB + t, xv);
     }
     __threadfence_system();
     __syncthreads();
@@ -770,22 +809,13 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
         __threadfence();
         __syncthreads();
         if (t == 0) st_release(pr.own + (Gn % DIST_RING), Gn + 1);
-        for (int q = 0; q < P; ++q) {
-            if (q == rank) continue;
-            double2* g0 = reinterpret_cast<double2*>(pr.slots[q] + next_off);
-            const double2* s0 = reinterpret_cast<const double2*>(sA);
-#pragma unroll
-            for (int e = t; e < IMG2; e += LU_THREADS) g0[e] = s0[e];
-            if (t < NB) pr.slots[q][next_off + NB * TS + t] = dinv[t];
-        }
+        store_image_all(pr, next_off, sA, dinv);
         if (t < 32) {       // y_{k+1} = L11^-1 b_{k+1}, part of the image every L-panel tile reads
             forward_rhs_warp(sC, rhs + (size_t)base * NB);
             __syncwarp();
             const double y0 = rhs[(size_t)base * NB + t], y1 = rhs[(size_t)base * NB + 32 + t];
-            for (int q = 0; q < P; ++q) {
-                pr.slots[q][next_off + PUB_DOUBLES + t] = y0;
-                pr.slots[q][next_off + PUB_DOUBLES + 32 + t] = y1;
-            }
+            store_slot_all(pr, next_off + PUB_DOUBLES + t, y0);
+            store_slot_all(pr, next_off + PUB_DOUBLES + 32 + t, y1);
         }
         __threadfence_system();
         __syncthreads();
@@ -876,6 +906,15 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
 
 static size_t dist_align(size_t v) { return (v + 255) / 256 * 256; }
 
+static int dist_slots(const Scene* s, int slots) {
+    const int nblk = s->ld / NB;
+    int S = slots < 2 ? 2 : slots;
+    if (S > DIST_RING / 2) S = DIST_RING / 2;
+    if (S > nblk) S = nblk < 2 ? 2 : nblk;
+    return S;
+}
+
+
 // mailbox layout: [slots | xbuf | flags | progress | xflags | own | counter, abort | stats]
 struct DistLayout {
     size_t slots, xbuf, flags, iflags, progress, xflags, own, misc, stats, total, slot_doubles;
@@ -914,6 +953,8 @@ static void dist_fill_peers(Scene* s, DistComm* c, int S) {
         p.progress[q] = b ? reinterpret_cast<int*>(b + L.progress) : nullptr;
         p.xflags[q] = b ? reinterpret_cast<int*>(b + L.xflags) : nullptr;
     }
+    p.mc_slots = c->mc ? reinterpret_cast<double*>(c->mc + L.slots) : nullptr;
+    p.mc_xbuf = c->mc ? reinterpret_cast<double*>(c->mc + L.xbuf) : nullptr;
     char* me = c->base[p.rank];
     p.own = reinterpret_cast<int*>(me + L.own);
     p.counter = reinterpret_cast<int*>(me + L.misc);
@@ -925,9 +966,8 @@ int dist_comm_create(Scene* s, int slots, unsigned char* handle64) {
     LLS_REQUIRE(s->dist == nullptr, LLS_ERR_STATE, "lls_dist_comm_create: the mailbox exists already");
     LLS_REQUIRE(s->cs.P <= DIST_MAX_P, LLS_ERR_UNSUPPORTED, "lls_dist_comm_create: at most 8 ranks (one box)");
     const int nblk = s->ld / NB;
-    int S = slots < 2 ? 2 : slots;
-    if (S > DIST_RING / 2) S = DIST_RING / 2;
-    if (S > nblk) S = nblk < 2 ? 2 : nblk;
+    const int S = dist_slots(s, slots);
+    (void)nblk;
     DistComm* c = new (std::nothrow) DistComm();
     LLS_REQUIRE(c != nullptr, LLS_ERR_ARG, "lls_dist_comm_create: out of host memory");
     const DistLayout L = dist_layout(s->ld, S);
@@ -970,6 +1010,44 @@ int dist_comm_create(Scene* s, int slots, unsigned char* handle64) {
     return LLS_OK;
 }
 
+size_t dist_comm_bytes(const Scene* s, int slots) { return dist_layout(s->ld, dist_slots(s, slots)).total; }
+
+// Mailboxes that belong to the caller: `bases` = the mailbox of every rank as mapped into this process (symmetric memory: same
+// size on every rank, zero-filled, bases[rank] = the own one), `mc` = the multicast mapping of all of them (or null).
+int dist_comm_attach(Scene* s, int slots, void* const* bases, void* mc) {
+    LLS_REQUIRE(s->dist == nullptr, LLS_ERR_STATE, "lls_dist_comm_attach: the mailbox exists already");
+    LLS_REQUIRE(s->cs.P <= DIST_MAX_P, LLS_ERR_UNSUPPORTED, "lls_dist_comm_attach: at most 8 ranks (one box)");
+    DistComm* c = new (std::nothrow) DistComm();
+    LLS_REQUIRE(c != nullptr, LLS_ERR_ARG, "lls_dist_comm_attach: out of host memory");
+    const int S = dist_slots(s, slots);
+    c->bytes = dist_layout(s->ld, S).total;
+    c->external = true;
+    for (int q = 0; q < s->cs.P; ++q) {
+        if (bases[q] == nullptr) {
+            delete c;
+            set_last_error(__FILE__, __LINE__, "lls_dist_comm_attach: null mailbox pointer");
+            return LLS_ERR_ARG;
+        }
+        c->base[q] = static_cast<char*>(bases[q]);
+    }
+    c->mc = static_cast<char*>(mc);
+    s->dist = c;
+    dist_fill_peers(s, c, S);
+    c->connected = true;
+    LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_owner_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+    LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_panel_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+    LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+    LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+    LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+    LLS_CUDA_TRY(cudaFuncSetAttribute(lu_dist_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES));
+    return LLS_OK;
+}
+
+int dist_comm_multicast(const Scene* s) {
+    const DistComm* c = static_cast<const DistComm*>(s->dist);
+    return (c != nullptr && c->mc != nullptr) ? 1 : 0;
+}
+
 int dist_comm_connect(Scene* s, const unsigned char* handles) {
     DistComm* c = static_cast<DistComm*>(s->dist);
     LLS_REQUIRE(c != nullptr, LLS_ERR_STATE, "lls_dist_comm_connect: call lls_dist_comm_create first");
@@ -996,7 +1074,7 @@ int dist_comm_destroy(Scene* s) {
     if (c == nullptr) return LLS_OK;
     for (int q = 0; q < DIST_MAX_P; ++q)
         if (c->opened[q]) cudaIpcCloseMemHandle(c->base[q]);
-    if (c->base[s->cs.rank]) cudaFree(c->base[s->cs.rank]);
+    if (!c->external && c->base[s->cs.rank]) cudaFree(c->base[s->cs.rank]);
     delete c;
     s->dist = nullptr;
     return LLS_OK;
@@ -1049,7 +1127,13 @@ int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st) 
         pair_min_rem = env != nullptr ? atoi(env) : -2;
     }
     int pair_min = pair_min_rem;
-    if (pair_min == -2) { pair_min = 64; while ((long long)pair_min * pair_min < 4096LL * P) pair_min += 8; }      // ~ 64 sqrt(P)
+    if (pair_min == -2) {
+        // ~ 64 sqrt(P); without the multicast mapping the thin launch of a pair exposes the owner's (P - 1)-fold panel push, which
+        // costs more than the pair returns beyond four ranks (measured on 8 B200s: 1.91 -> 1.99 s per solve at N = 32,000)
+        pair_min = 64;
+        while ((long long)pair_min * pair_min < 4096LL * P) pair_min += 8;
+        if (c->mc == nullptr && P > 4) pair_min = 0;
+    }
     if (fused_steps) {
         // launch(k, passes, thin): tiles with block rows / columns >= k + passes take panels k .. k + passes - 1, roles factor panel k + passes
         auto launch = [&](int k, int passes, int thin) {

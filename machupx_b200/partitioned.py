@@ -247,6 +247,9 @@ class PartitionedDeviceScene:
         import torch.distributed as dist
         if os.environ.get("LLS_PARTITIONED_P2P", "1") != "1":
             return False
+        self.multicast = False
+        if self.world > 1 and os.environ.get("LLS_PARTITIONED_SYMM", "1") == "1" and self._attach_symmetric_memory(group):
+            return True
         ok = 1
         handle = (ctypes.c_ubyte * 64)()
         try:
@@ -272,6 +275,47 @@ class PartitionedDeviceScene:
             self._native.check(self.lib.lls_dist_comm_destroy(self.handle))
         return bool(ok)
 
+    def _attach_symmetric_memory(self, group):
+        """Preferred plumbing of the mailboxes: torch.distributed's symmetric memory (every rank's buffer mapped into every process,
+        plus -- on NVSwitch systems -- ONE multicast mapping of all of them, NVLS).  With the multicast mapping an owner kernel stores
+        a panel once and the switch replicates it into all mailboxes.  Returns False on every rank if any rank cannot (old driver, no
+        fabric support, API missing): the caller then falls back to CUDA IPC handles (unicast stores to every peer)."""
+        torch = self.torch
+        import torch.distributed as dist
+        slots = int(os.environ.get("LLS_PARTITIONED_SLOTS", "8"))
+        ok, hdl, buf = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = ctypes.c_size_t(0)
+            self._call(self.lib.lls_dist_comm_bytes, slots, ctypes.byref(nbytes))
+            with torch.cuda.device(self.device):
+                buf = symm.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
+                buf.zero_()
+                torch.cuda.synchronize(self.device)
+                grp = group if group is not None else dist.group.WORLD
+                hdl = symm.rendezvous(buf, grp)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or int(hdl.rank) != self.rank or ptrs[self.rank] != buf.data_ptr():
+                raise RuntimeError("symmetric memory handle does not match the process group")
+        except Exception as exc:   # noqa: BLE001
+            ok, self.exchange_error = 0, "symmetric memory: " + repr(exc)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            return False
+        use_mc = os.environ.get("LLS_PARTITIONED_MULTICAST", "1") == "1" and bool(getattr(hdl, "has_multicast_support", False))
+        mc = int(hdl.multicast_ptr) if use_mc else 0
+        flag = torch.tensor([1 if mc else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)          # multicast on every rank or on none
+        if int(flag.item()) == 0:
+            mc = 0
+        arr = (ctypes.c_void_p * self.world)(*ptrs)
+        self._call(self.lib.lls_dist_comm_attach, slots, arr, ctypes.c_void_p(mc) if mc else None)
+        dist.barrier(group=group)                                         # every mailbox is zero-filled and attached before anyone stores
+        self._symm = (buf, hdl)                                           # keep the mappings alive as long as the scene
+        self.multicast = bool(mc)
+        return True
+
     def lu_solve_fused(self):
         self._call(self.lib.lls_dist_lu_solve, self._st())
 
@@ -286,6 +330,7 @@ class PartitionedDeviceScene:
             if getattr(self, "handle", None):
                 self.lib.lls_destroy(self.handle)
                 self.handle = None
+            self._symm = None
         except Exception:
             pass
 

@@ -39,7 +39,7 @@ for name in names:
     if rank == 0:
         print(json.dumps({"fixture": name, "world": world, "n": int(tables["n"]), "ld": dev.ld, "gamma_rel_err": e_g, "force_rel_err": e_f,
                           "iterations": it, "reference_iterations": int(meta["iterations"]), "final_error": err, "status": status,
-                          "solve_s": t2 - t1, "first_solve_s": t1 - t0, "fused_exchange": bool(dev.fused_exchange),
+                          "solve_s": t2 - t1, "first_solve_s": t1 - t0, "fused_exchange": bool(dev.fused_exchange), "multicast": bool(getattr(dev, "multicast", False)), "exchange_error": getattr(dev, "exchange_error", None),
                           "exchange_stats": dev.exchange_stats() if dev.fused_exchange else None, "ok": bool(good)}), flush=True)
     del dev
 if world > 1:

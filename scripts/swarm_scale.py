@@ -53,7 +53,7 @@ out = {"world": world, "control_points": scene._N, "ld": dev.ld, "aircraft": sce
        "CL_first_last": [FM[k]["total"]["CL"] for k in (list(FM)[0], list(FM)[-1])],
        "CL_sum": float(sum(v["total"]["CL"] for v in FM.values())), "CD_sum": float(sum(v["total"]["CD"] for v in FM.values())),
        "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "phase_ms": tm,
-       "fused_exchange": bool(dev.fused_exchange), "exchange_stats": dev.exchange_stats() if dev.fused_exchange else None}
+       "fused_exchange": bool(dev.fused_exchange), "multicast": bool(getattr(dev, "multicast", False)), "exchange_error": getattr(dev, "exchange_error", None), "exchange_stats": dev.exchange_stats() if dev.fused_exchange else None}
 try:
     off = ctypes.c_size_t(0) if "ctypes" in dir() else None
     import ctypes as _ct
