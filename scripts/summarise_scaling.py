@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RAW = os.path.join(ROOT, "profiles", "r2_raw")
-pick = sys.argv[1:] or ["scale2_bench_n1.json", "scale2b_bench_n2.json", "scale8b_bench_n4.json", "scale8b_bench_n8.json"]
+pick = sys.argv[1:] or ["scale2_bench_n1.json", "scale2b_bench_n2.json", "scale8c_bench_n4.json", "scale8c_bench_n8.json"]
 rows = []
 for name in pick:
     path = os.path.join(RAW, name)
@@ -20,7 +20,7 @@ for name in pick:
                  "solves_per_s": d["value"], "ms_per_solve": d["ms_per_step"], "e2e_solves_per_s": d["e2e"]["value"],
                  "lu_ms_per_solve": d["phase_ms"]["lu"], "lu_tflops_per_gpu": d["roofline"]["achieved"], "dmma_peak_tflops": d["roofline"]["peak"],
                  "newton_iterations": d["per_rank_newton_iterations"], "max_panel_wait_ms_per_solve": max(w[0] for w in waits) if waits else None,
-                 "exchange": d["exchange"]["path"], "CL_sum": d["parity"]["CL_sum"], "final_residual": d["parity"]["final_residual"],
+                 "exchange": d["exchange"]["path"], "multicast": d["exchange"].get("multicast"), "CL_sum": d["parity"]["CL_sum"], "final_residual": d["parity"]["final_residual"],
                  "sm_mhz": (d.get("clocks") or {}).get("sm_mhz"), "throttle_reasons": (d.get("clocks") or {}).get("reasons")})
 base = next((r for r in rows if r["n_gpus"] == 1), None)
 for r in rows:
