@@ -42,10 +42,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one lu_step_kernel launch (block step k = 8 of an N = 4000 factorisation,
-# 54 x 54 = 2916 tiles) from the `ncu --set full` capture summarised in profiles/r1_lu_step_full.txt.  Algorithmic bytes
-# of that launch: read + write of the trailing matrix, 2 x 8 x (54 x 64)^2 = 191 MB; the 126 MB L2 keeps part of it.
-NCU_LU_TRAFFIC = {"bytes_per_launch": 138.1e6, "algorithmic_bytes_per_launch": 191.1e6,
-                  "launch": "lu_step_kernel, block step 8 of 63 (2916 tiles) at N=4000", "source": "profiles/r1_lu_step_full.txt"}
+# 54 x 54 = 2916 tiles) from the `ncu --set full` capture summarised in profiles/r2_lu_step_full.txt (99.46 MB read + 38.28 MB
+# written; round 1: 138.1 MB).  Algorithmic bytes of that launch: read + write of the trailing matrix, 2 x 8 x (54 x 64)^2 = 191 MB;
+# the 126 MB L2 keeps part of it.
+NCU_LU_TRAFFIC = {"bytes_per_launch": 137.7e6, "algorithmic_bytes_per_launch": 191.1e6,
+                  "launch": "lu_step_kernel, block step 8 of 63 (2916 tiles) at N=4000", "source": "profiles/r2_lu_step_full.txt"}
 METRIC = "lifting-line solves/sec"
 UNIT = "solves/s"
 
