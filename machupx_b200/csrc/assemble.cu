@@ -109,10 +109,70 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// everything of a residual row after v_i: section lift (scene.py:732-791), R_i (scene.py:723), the row vectors of the Jacobian.
+// Per-case pointers already applied by the caller.
+__device__ __forceinline__ void residual_row_tail(int i, const Vec3& vi, int ld, int flags, const double* __restrict__ tab,
+                                                  const int32_t* __restrict__ itab, const double* __restrict__ af, double* __restrict__ W,
+                                                  double* __restrict__ out, double* __restrict__ partial, int* __restrict__ status_case) {
+    const double* gamma = out + (size_t)LLS_O_GAMMA * ld;
+    const double gam = gamma[i];
+    const Vec3 dl = ld3(tab, ld, LLS_F_DL, i);
+    const Vec3 w = cross(vi, dl);                                                 // scene.py:715-717
+    const double wmag = norm(w);
+    const double L_vortex = 2.0 * wmag * gam;
+    const Vec3 us = ld3(tab, ld, LLS_F_US, i), ua = ld3(tab, ld, LLS_F_UA, i), un = ld3(tab, ld, LLS_F_UN, i);
+    const bool in_plane = flags & LLS_FLAG_IN_PLANE, total = flags & LLS_FLAG_TOTAL_VELOCITY;
+    const bool swept = flags & LLS_FLAG_SWEPT_SECTIONS, pro = flags & LLS_FLAG_MATCH_MACHUP_PRO;
+    const Vec3 vref = in_plane ? (vi - dot(us, vi) * us) : vi;                    // scene.py:737-745
+    const double V2 = dot(vref, vref), Vmag = sqrt(V2);
+    const double cbar = tab[(size_t)LLS_F_CBAR * ld + i], nu = tab[(size_t)LLS_F_NU * ld + i], sos = tab[(size_t)LLS_F_SOS * ld + i];
+    const double Re = Vmag * cbar / nu, Mach = Vmag / sos;
+    const double va = dot(vi, ua), vn = dot(vi, un);                              // scene.py:751-753
+    const double alpha = atan2(vn, va);
+    const SectionParams sp = load_section(tab, itab, af, ld, i);
+    bool oob = false;
+    const double CLa = section_CLa(sp, alpha, Re, Mach);                          // scene.py:765-768
+    double CL = section_CL(sp, alpha, Re, Mach, oob);
+    const double CLRe = section_CLRe(sp, alpha, Re, Mach), CLM = section_CLM(sp, alpha, Re, Mach);
+    if (oob) atomicOr(status_case, LLS_STATUS_SECTION_BOUNDS);
+    const double dS = tab[(size_t)LLS_F_DS * ld + i];
+    const double Vinf = W[(size_t)W_VINF_MAG * ld + i];
+    const double Vfix = in_plane ? W[(size_t)W_VINF_IP * ld + i] : Vinf;
+    double L_section, scale;
+    if (pro) {                                                                    // scene.py:774-775
+        L_section = Vinf * Vinf * CL * dS;
+    } else {
+        if (swept) {                                                              // scene.py:778-779, 797
+            const double aL0 = out[(size_t)LLS_O_AL0 * ld + i];
+            CL += CLa * (aL0 - aL0 * tab[(size_t)LLS_F_CSWI * ld + i]);
+        }
+        L_section = (total ? V2 : Vfix * Vfix) * CL * dS;                         // scene.py:782-791
+    }
+    scale = (total ? V2 : Vfix * Vfix) * dS;                                      // scene.py:881-890
+    const double R = L_vortex - L_section;                                        // scene.py:723
+    // per-control-point results other code reads after a solve
+    st3(out, ld, LLS_O_VI, i, vi);
+    out[(size_t)LLS_O_ALPHA * ld + i] = alpha;
+    out[(size_t)LLS_O_CL * ld + i] = CL;
+    out[(size_t)LLS_O_RE * ld + i] = Re;
+    out[(size_t)LLS_O_MACH * ld + i] = Mach;
+    out[(size_t)LLS_O_R * ld + i] = R;
+    partial[i] = R * R;
+    // Jacobian row data (scene.py:867-893)
+    st3(W, ld, W_WS, i, (2.0 * gam / wmag) * w);
+    const double c2 = total ? 2.0 * dS * CL : 0.0;
+    const double c3 = scale * CLa / (vn * vn + va * va);
+    const double c4 = scale * CLRe / (nu * Vmag), c5 = scale * CLM / (sos * Vmag);
+    st3(W, ld, W_G, i, (c2 + c5) * vref + c3 * (va * un - vn * ua));
+    st3(W, ld, W_E, i, c4 * vref);
+    W[(size_t)W_DIAG * ld + i] = 2.0 * wmag;
+    W[(size_t)W_RHS * ld + i] = -R;                                               // scene.py:896
+}
+
 // THREADS threads share a row; ROWS rows per CTA.  ROWS > 1 needs THREADS == 32 (one warp per row, reduction by shuffles only): the
 // shape for the small scenes of large batches, where a row is shorter than a CTA and the scalar tail of the row (section lift,
 // Jacobian row vectors) is what there is to hide.
-template <int THREADS, int ROWS = 1>
+template <int THREADS, int ROWS = 1, bool TAIL = true>
 __global__ void __launch_bounds__(THREADS * ROWS) residual_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                            const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                            const double* __restrict__ V, double* __restrict__ W,
@@ -163,62 +223,27 @@ __global__ void __launch_bounds__(THREADS * ROWS) residual_kernel(int n, int ld,
         return;
     }
     const Vec3 vi = ld3(W, ld, W_VIR, i) + Vec3{sx, sy, sz};                       // scene.py:728
-    if (vel_only) {  // integration pre-pass of a linear solve: only v_i is refreshed (scene.py:943)
+    if (vel_only || !TAIL) {  // integration pre-pass of a linear solve (scene.py:943), or the tail runs as a kernel of its own
         st3(out, ld, LLS_O_VI, i, vi);
         return;
     }
-    const double gam = gamma[i];
-    const Vec3 dl = ld3(tab, ld, LLS_F_DL, i);
-    const Vec3 w = cross(vi, dl);                                                 // scene.py:715-717
-    const double wmag = norm(w);
-    const double L_vortex = 2.0 * wmag * gam;
-    const Vec3 us = ld3(tab, ld, LLS_F_US, i), ua = ld3(tab, ld, LLS_F_UA, i), un = ld3(tab, ld, LLS_F_UN, i);
-    const bool in_plane = flags & LLS_FLAG_IN_PLANE, total = flags & LLS_FLAG_TOTAL_VELOCITY;
-    const bool swept = flags & LLS_FLAG_SWEPT_SECTIONS, pro = flags & LLS_FLAG_MATCH_MACHUP_PRO;
-    const Vec3 vref = in_plane ? (vi - dot(us, vi) * us) : vi;                    // scene.py:737-745
-    const double V2 = dot(vref, vref), Vmag = sqrt(V2);
-    const double cbar = tab[(size_t)LLS_F_CBAR * ld + i], nu = tab[(size_t)LLS_F_NU * ld + i], sos = tab[(size_t)LLS_F_SOS * ld + i];
-    const double Re = Vmag * cbar / nu, Mach = Vmag / sos;
-    const double va = dot(vi, ua), vn = dot(vi, un);                              // scene.py:751-753
-    const double alpha = atan2(vn, va);
-    const SectionParams sp = load_section(tab, itab, af, ld, i);
-    bool oob = false;
-    const double CLa = section_CLa(sp, alpha, Re, Mach);                          // scene.py:765-768
-    double CL = section_CL(sp, alpha, Re, Mach, oob);
-    const double CLRe = section_CLRe(sp, alpha, Re, Mach), CLM = section_CLM(sp, alpha, Re, Mach);
-    if (oob) atomicOr(case_work_ptr(status, cs.work), LLS_STATUS_SECTION_BOUNDS);
-    const double dS = tab[(size_t)LLS_F_DS * ld + i];
-    const double Vinf = W[(size_t)W_VINF_MAG * ld + i];
-    const double Vfix = in_plane ? W[(size_t)W_VINF_IP * ld + i] : Vinf;
-    double L_section, scale;
-    if (pro) {                                                                    // scene.py:774-775
-        L_section = Vinf * Vinf * CL * dS;
-    } else {
-        if (swept) {                                                              // scene.py:778-779, 797
-            const double aL0 = out[(size_t)LLS_O_AL0 * ld + i];
-            CL += CLa * (aL0 - aL0 * tab[(size_t)LLS_F_CSWI * ld + i]);
-        }
-        L_section = (total ? V2 : Vfix * Vfix) * CL * dS;                         // scene.py:782-791
-    }
-    scale = (total ? V2 : Vfix * Vfix) * dS;                                      // scene.py:881-890
-    const double R = L_vortex - L_section;                                        // scene.py:723
-    // per-control-point results other code reads after a solve
-    st3(out, ld, LLS_O_VI, i, vi);
-    out[(size_t)LLS_O_ALPHA * ld + i] = alpha;
-    out[(size_t)LLS_O_CL * ld + i] = CL;
-    out[(size_t)LLS_O_RE * ld + i] = Re;
-    out[(size_t)LLS_O_MACH * ld + i] = Mach;
-    out[(size_t)LLS_O_R * ld + i] = R;
-    partial[i] = R * R;
-    // Jacobian row data (scene.py:867-893)
-    st3(W, ld, W_WS, i, (2.0 * gam / wmag) * w);
-    const double c2 = total ? 2.0 * dS * CL : 0.0;
-    const double c3 = scale * CLa / (vn * vn + va * va);
-    const double c4 = scale * CLRe / (nu * Vmag), c5 = scale * CLM / (sos * Vmag);
-    st3(W, ld, W_G, i, (c2 + c5) * vref + c3 * (va * un - vn * ua));
-    st3(W, ld, W_E, i, c4 * vref);
-    W[(size_t)W_DIAG * ld + i] = 2.0 * wmag;
-    W[(size_t)W_RHS * ld + i] = -R;                                               // scene.py:896
+    residual_row_tail(i, vi, ld, flags, tab, itab, af, W, out, partial, case_work_ptr(status, cs.work));
+}
+
+// The tail of every row as one THREAD per row (batches of small scenes): all table reads are coalesced along i and no lane idles,
+// where the fused kernel leaves the whole tail to one lane of the row's warp.
+__global__ void __launch_bounds__(128) residual_tail_kernel(int n, int ld, int flags, const double* __restrict__ tab,
+                                                            const int32_t* __restrict__ itab, const double* __restrict__ af,
+                                                            double* __restrict__ W, double* __restrict__ out, double* __restrict__ partial,
+                                                            int* __restrict__ status, CaseStrides cs) {
+    if (LLS_CASE_INACTIVE(cs)) return;
+    tab = case_ptr(tab, cs.tab);
+    W = case_work_ptr(W, cs.work);
+    out = case_ptr(out, cs.out);
+    partial = case_work_ptr(partial, cs.work);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    residual_row_tail(i, ld3(out, ld, LLS_O_VI, i), ld, flags, tab, itab, af, W, out, partial, case_work_ptr(status, cs.work));
 }
 
 // deterministic sum of partial[0..n) -> scalars[slot]
@@ -273,8 +298,14 @@ int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked) {
     const int rows = s->cs.P == 1 ? s->n : s->n_loc_blocks * 64;
     if (s->ld <= 512 && s->ncases > 1) {
         // small scenes in large batches: one warp per row, 8 rows per CTA
-        residual_kernel<32, 8><<<dim3((rows + 7) / 8, 1, s->ncases), 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out,
-                                                                                s->partial, vel_only, s->status, strides(s, masked));
+        // ... and the tail of the rows as a kernel of its own, one thread per row
+        residual_kernel<32, 8, false><<<dim3((rows + 7) / 8, 1, s->ncases), 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W,
+                                                                                       s->out, s->partial, vel_only, s->status, strides(s, masked));
+        if (!vel_only) {
+            residual_tail_kernel<<<dim3((s->n + 127) / 128, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out,
+                                                                                      s->partial, s->status, strides(s, masked));
+            count_launch();
+        }
     } else {
         residual_kernel<128><<<dim3(rows, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
                                                                       vel_only, s->status, strides(s, masked));
