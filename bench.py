@@ -769,6 +769,11 @@ def run_ours(args):
                                       "1 BLAS thread (machupX/__init__.py:1-6): %.1f s.  `bench.py --impl reference` adds the all-cores setting."
                                       % (ref["construct_s"], a["seconds_per_solve"]),
                             "seconds_per_solve": a["seconds_per_solve"], "construct_s": ref["construct_s"],
+                            "vji_pair_evals_per_s": {"per_solve_part_only": float(n) * n / a["vji_flow_seconds"] if a.get("vji_flow_seconds") else None,
+                                                     "with_construction": float(n) * n / (a["vji_flow_seconds"] + ref["construct_s"]) if a.get("vji_flow_seconds") else None,
+                                                     "note": "the reference builds V_ji in two places: the bound / joint segments at scene construction "
+                                                             "(scene.py:522-541, inside the construction time) and the trailing legs in every solve "
+                                                             "(_calc_invariant_flow_properties, scene.py:612-634); the GPU figure (kernels.vji_build) is all five segments"},
                             "reference_CL": a["CL"], "fixture_CL": meta["FM"][list(meta["FM"])[0]]["total"]["CL"]}
         else:
             cpu_v, cpu_total, cpu_parts = cpu_sample(tables, ac_state, meta, threads)
