@@ -211,8 +211,8 @@ class PartitionedDeviceScene:
         self.comm = TorchComm(group, dev) if dist.is_initialized() and shard is None else LocalComm()
         self.fused_exchange = self._connect_mailboxes(group) if shard is None else False
         self.solver = PartitionedSolver(self, self.comm, self.nblk, self.world, self.rank)
-        # One factorisation + back substitution = 3 launches and 1-2 broadcasts per block step, thousands of tiny host calls:
-        # after a warm-up pass it is captured into a CUDA graph (NCCL broadcasts included) and replayed.
+        # Step-wise fall-back path only (LLS_PARTITIONED_P2P=0 or no peer access): one factorisation + back substitution = 3 launches
+        # and 1-2 NCCL broadcasts per block step issued from here; optionally captured into a CUDA graph after a warm-up pass.
         self.use_graph = os.environ.get("LLS_PARTITIONED_GRAPH", "0") == "1"   # off by default: capture with NCCL hung on the 2-GPU box (round 1)
         self._lu_graph = None
         self._lu_calls = 0
