@@ -263,6 +263,16 @@ int lls_dist_lu_solve(lls_scene* h, void* stream);
 int lls_dist_comm_stats(lls_scene* h, double* out4, void* stream);
 int lls_dist_comm_destroy(lls_scene* h);
 
+/* The launch schedule of lls_dist_lu_solve as data (pure host code: callable without a GPU; tests/test_dist_schedule_cpu.py checks
+ * with it that every tile of every rank receives every panel exactly once, in order, and that every panel is factored / solved once).
+ *   lls_dist_debug_schedule : the launches of one factorisation of `rank` in order, 9 ints each {k, passes, thin, base, rem, lb0, nloc,
+ *                             own, grid}: tiles with block rows / columns >= base = k + passes take panels k .. k + passes - 1 and the
+ *                             roles factor panel `base`; pair_min_rem >= 0: threshold of the rank-128 pairs, -1 / -2: the default with /
+ *                             without a multicast mapping.  Returns the number of launches (out9 may be NULL), -1 on bad arguments.
+ *   lls_dist_debug_role     : block index of a launch -> role (0 DIAG, 1 UROW, 2 LCOL, 3 OTHER, 4 none) and its tile. */
+int lls_dist_debug_schedule(int nblk, int world, int rank, int pair_min_rem, int* out9, int max_launches);
+int lls_dist_debug_role(int block, int own, int rem, int base, int lb0, int nloc, int thin, int* local_block_row, int* block_col);
+
 /* Per-aircraft flight state, n_aircraft * LLS_AC_STRIDE doubles on the device
  * (reference: Airplane.set_state airplane.py:105-213 -> scene.py:562-582). */
 int lls_set_state(lls_scene* h, const double* d_ac_state);

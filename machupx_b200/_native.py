@@ -52,6 +52,8 @@ SIGNATURES = {
     "lls_dist_lu_solve": (_i, [_vp, _vp]),
     "lls_dist_comm_stats": (_i, [_vp, _pd, _vp]),
     "lls_dist_comm_destroy": (_i, [_vp]),
+    "lls_dist_debug_schedule": (_i, [_i, _i, _i, _i, _pi, _i]),
+    "lls_dist_debug_role": (_i, [_i, _i, _i, _i, _i, _i, _i, _pi, _pi]),
     "lls_set_state": (_i, [_vp, _vp]),
     "lls_flow_state": (_i, [_vp, _vp]),
     "lls_build_influence": (_i, [_vp, _d, _vp]),

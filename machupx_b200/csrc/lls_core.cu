@@ -446,6 +446,15 @@ extern "C" int lls_dist_comm_attach(lls_scene* h, int slots, void* const* d_mail
 
 extern "C" int lls_dist_comm_multicast(lls_scene* h) { return (h != nullptr) ? dist_comm_multicast(h) : 0; }
 
+extern "C" int lls_dist_debug_schedule(int nblk, int world, int rank, int pair_min_rem, int* out9, int max_launches) {
+    return dist_debug_schedule(nblk, world, rank, pair_min_rem, out9, max_launches);
+}
+
+extern "C" int lls_dist_debug_role(int block, int own, int rem, int base, int lb0, int nloc, int thin, int* local_block_row, int* block_col) {
+    if (local_block_row == nullptr || block_col == nullptr) return -1;
+    return dist_debug_role(block, own, rem, base, lb0, nloc, thin, local_block_row, block_col);
+}
+
 extern "C" int lls_dist_comm_connect(lls_scene* h, const unsigned char* all_handles) {
     LLS_CHECK_BOUND(h);
     LLS_REQUIRE(all_handles != nullptr || h->cs.P == 1, LLS_ERR_ARG, "lls_dist_comm_connect: null handles");

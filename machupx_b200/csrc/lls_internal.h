@@ -149,6 +149,8 @@ int dist_comm_connect(Scene* s, const unsigned char* handles);
 size_t dist_comm_bytes(const Scene* s, int slots);
 int dist_comm_attach(Scene* s, int slots, void* const* bases, void* mc);
 int dist_comm_multicast(const Scene* s);
+int dist_debug_schedule(int nblk, int P, int rank, int pair_min, int* out, int max_launches);
+int dist_debug_role(int b, int own, int rem, int base, int lb0, int nloc, int thin, int* lb, int* bj);
 int dist_comm_destroy(Scene* s);
 int dist_comm_stats(Scene* s, double* out4, cudaStream_t st);
 int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st);

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace lls {
 
@@ -693,6 +694,75 @@ __global__ void __launch_bounds__(NB) lu_dist_backsolve_p2p_kernel(const double*
 // So the exchange of panel k+1 and every panel solve run underneath the DMMA bulk of step k; a launch waits for nothing but the
 // "panel k complete" flag that was released while launch k-1 was still running.  FIRST (k = -1): no update, panel 0 only.
 // Grid order: DIAG, UROW (owner only), LCOL, OTHER -- producers of a flag are resident before anything on this GPU can wait on it.
+
+// ---- the schedule of the fused-step factorisation, shared by the launcher, the kernel and the CPU tests (lls_dist_debug_*) -----------
+// One launch of a rank: tiles with block rows / columns >= base = k + passes take panels k .. k + passes - 1, the roles factor / solve
+// panel `base`.  thin: the grid stops after the panel roles.
+struct DistLaunch {
+    int k, passes, thin;      // first panel applied (-1: the first launch, nothing to apply), panels per visit, roles only
+    int base, rem;            // first block row / column of the trailing matrix handled, and its size in blocks
+    int lb0, nloc;            // first local block row with global index >= base, number of such local block rows
+    int own;                  // this rank owns block row `base` (its local block lb0)
+    long long grid;           // CTAs
+};
+__host__ __device__ inline DistLaunch dist_launch(int k, int passes, int thin, int nblk, int P, int rank, int n_loc_blocks) {
+    DistLaunch L;
+    L.k = k; L.passes = passes; L.thin = thin;
+    L.base = k + passes;
+    L.rem = nblk - L.base;
+    L.lb0 = (L.base - rank + P - 1) / P;
+    if (L.lb0 < 0) L.lb0 = 0;
+    L.nloc = n_loc_blocks - L.lb0 > 0 ? n_loc_blocks - L.lb0 : 0;
+    L.own = (L.base % P == rank) ? 1 : 0;
+    const int below = L.nloc - L.own;
+    L.grid = L.own + (L.own ? L.rem - 1 : 0) + below + ((k >= 0 && !thin) ? (long long)below * (L.rem - 1) : 0);
+    if (L.grid < 1) L.grid = 1;
+    return L;
+}
+enum DistRole { DIST_DIAG = 0, DIST_UROW = 1, DIST_LCOL = 2, DIST_OTHER = 3, DIST_NONE = 4 };
+// block index -> role and tile (local block row lb, global block column bj).  Grid order: DIAG, UROW (owner only), LCOL, OTHER.
+__host__ __device__ inline int dist_role(int b, int own, int rem, int base, int lb0, int nloc, int thin, int& lb, int& bj) {
+    const int nd = own ? 1 : 0, nu = own ? rem - 1 : 0;
+    const int rows_below = nloc - nd;               // local block rows with global index > base
+    if (b < nd) { lb = lb0; bj = base; return DIST_DIAG; }
+    if (b < nd + nu) { lb = lb0; bj = base + 1 + (b - nd); return DIST_UROW; }
+    if (b < nd + nu + rows_below) { lb = lb0 + nd + (b - nd - nu); bj = base; return DIST_LCOL; }
+    const int o = b - nd - nu - rows_below;
+    if (thin || rem <= 1 || o >= rows_below * (rem - 1)) { lb = -1; bj = -1; return DIST_NONE; }   // the launch only reported progress
+    lb = lb0 + nd + o / (rem - 1);
+    bj = base + 1 + o % (rem - 1);
+    return DIST_OTHER;
+}
+// default threshold of the rank-128 pairs: ~ 64 sqrt(P) block rows; without the multicast mapping the thin launch of a pair exposes
+// the owner's (P - 1)-fold panel push, which costs more than the pair returns beyond four ranks (8 B200s: 1.91 -> 1.99 s at N = 32,000)
+inline int dist_default_pair_min(int P, bool multicast) {
+    int pair_min = 64;
+    while ((long long)pair_min * pair_min < 4096LL * P) pair_min += 8;
+    if (!multicast && P > 4) pair_min = 0;
+    return pair_min;
+}
+// the launches of one factorisation of a rank, in order; returns their number (out may be null)
+inline int dist_schedule(int nblk, int P, int rank, int n_loc_blocks, int pair_min, DistLaunch* out, int max_out) {
+    int n = 0;
+    auto add = [&](int k, int passes, int thin) {
+        if (out != nullptr && n < max_out) out[n] = dist_launch(k, passes, thin, nblk, P, rank, n_loc_blocks);
+        ++n;
+    };
+    add(-1, 1, 0);                                      // panel 0
+    for (int k = 0; k + 1 < nblk;) {
+        const int rem = nblk - 1 - k;                   // block rows of the trailing matrix after step k
+        if (pair_min > 0 && rem >= pair_min && k + 2 < nblk) {
+            add(k, 1, 1);                               // thin: block row / column k + 1 take panel k, panel k + 1 factored and exchanged
+            add(k, 2, 0);                               // the rest takes panels k and k + 1 in one visit, panel k + 2 on the way
+            k += 2;
+        } else {
+            add(k, 1, 0);
+            k += 1;
+        }
+    }
+    return n;
+}
+
 // arrival of a whole panel: every owner CTA (1 DIAG + rem - 1 UROW) calls this from one thread AFTER fencing its stores at system
 // scope and synchronising; the last one to arrive releases the "panel complete" flags in every rank's mailbox
 __device__ __forceinline__ void dist_arrive(const DistPeers& pr, int rem, int Gn) {
@@ -726,20 +796,10 @@ __global__ void __launch_bounds__(LU_THREADS, 3) lu_dist_step_kernel(double* __r
     const int Gc = Gn - PASSES;                         // global index of panel k (not FIRST); panel k + 1 is Gc + 1
     if (b == 0 && t < P) st_release_sys(pr.progress[t] + rank, FIRST ? Gn : Gc);    // every global step below this one is consumed here
     const bool own = (base % P == rank);                // this rank owns block row base: its local block lb0
-    enum { DIAG, UROW, LCOL, OTHER } role;
+    constexpr int DIAG = DIST_DIAG, UROW = DIST_UROW, LCOL = DIST_LCOL, OTHER = DIST_OTHER;
     int lb, bj;
-    {
-        const int nd = own ? 1 : 0, nu = own ? rem - 1 : 0;
-        const int rows_below = nloc - nd;               // local block rows with global index > base
-        if (b < nd) { role = DIAG; lb = lb0; bj = base; }
-        else if (b < nd + nu) { role = UROW; lb = lb0; bj = base + 1 + (b - nd); }
-        else if (b < nd + nu + rows_below) { role = LCOL; lb = lb0 + nd + (b - nd - nu); bj = base; }
-        else {
-            const int o = b - nd - nu - rows_below;
-            if (thin || rem <= 1 || o >= rows_below * (rem - 1)) return;       // nothing (left) for this rank: the launch only reported progress
-            role = OTHER; lb = lb0 + nd + o / (rem - 1); bj = base + 1 + o % (rem - 1);
-        }
-    }
+    const int role = dist_role(b, own ? 1 : 0, rem, base, lb0, nloc, thin, lb, bj);
+    if (role == DIST_NONE) return;                      // nothing (left) for this rank: the launch only reported progress
     const int bi = lb * P + rank;                       // global block row
     double* gC = Mloc + (size_t)lb * NB * ld + (size_t)bj * NB;
     constexpr int IMG2 = NB * TS / 2;
@@ -1126,49 +1186,24 @@ int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st) 
         const char* env = getenv("LLS_PARTITIONED_PAIR_MIN_REM");
         pair_min_rem = env != nullptr ? atoi(env) : -2;
     }
-    int pair_min = pair_min_rem;
-    if (pair_min == -2) {
-        // ~ 64 sqrt(P); without the multicast mapping the thin launch of a pair exposes the owner's (P - 1)-fold panel push, which
-        // costs more than the pair returns beyond four ranks (measured on 8 B200s: 1.91 -> 1.99 s per solve at N = 32,000)
-        pair_min = 64;
-        while ((long long)pair_min * pair_min < 4096LL * P) pair_min += 8;
-        if (c->mc == nullptr && P > 4) pair_min = 0;
-    }
+    const int pair_min = (pair_min_rem == -2) ? dist_default_pair_min(P, c->mc != nullptr) : pair_min_rem;
     if (fused_steps) {
-        // launch(k, passes, thin): tiles with block rows / columns >= k + passes take panels k .. k + passes - 1, roles factor panel k + passes
-        auto launch = [&](int k, int passes, int thin) {
-            const int base = k + passes, rem = nblk - base;
-            int lb0 = (base - rank + P - 1) / P;           // first local block whose global index lb * P + rank is >= base
-            if (lb0 < 0) lb0 = 0;
-            const int nloc = s->n_loc_blocks - lb0 > 0 ? s->n_loc_blocks - lb0 : 0;
-            const bool own = (base % P == rank);
-            const int nd = own ? 1 : 0, below = nloc - nd;
-            long long grid = nd + (own ? rem - 1 : 0) + below + ((k >= 0 && !thin) ? (long long)below * (rem - 1) : 0);
-            if (grid < 1) grid = 1;
-            const int Gn = (int)(G0 + base);
-            if (k < 0) {
-                lu_dist_step_kernel<true, 1><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
-                                                                                                s->scalars, s->status, thin);
-            } else if (passes == 1) {
-                lu_dist_step_kernel<false, 1><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
-                                                                                                 s->scalars, s->status, thin);
+        const int nlaunch = dist_schedule(nblk, P, rank, s->n_loc_blocks, pair_min, nullptr, 0);
+        std::vector<DistLaunch> plan((size_t)nlaunch);
+        dist_schedule(nblk, P, rank, s->n_loc_blocks, pair_min, plan.data(), nlaunch);
+        for (const DistLaunch& L : plan) {
+            const int Gn = (int)(G0 + L.base);
+            if (L.k < 0) {
+                lu_dist_step_kernel<true, 1><<<(unsigned)L.grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, L.k, nblk, L.lb0, L.nloc, rhs, pr, Gn, s->uinv,
+                                                                                                  s->scalars, s->status, L.thin);
+            } else if (L.passes == 1) {
+                lu_dist_step_kernel<false, 1><<<(unsigned)L.grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, L.k, nblk, L.lb0, L.nloc, rhs, pr, Gn, s->uinv,
+                                                                                                   s->scalars, s->status, L.thin);
             } else {
-                lu_dist_step_kernel<false, 2><<<(unsigned)grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, k, nblk, lb0, nloc, rhs, pr, Gn, s->uinv,
-                                                                                                 s->scalars, s->status, thin);
+                lu_dist_step_kernel<false, 2><<<(unsigned)L.grid, LU_THREADS, 2 * TILE_BYTES, st>>>(s->M, s->ld, L.k, nblk, L.lb0, L.nloc, rhs, pr, Gn, s->uinv,
+                                                                                                   s->scalars, s->status, L.thin);
             }
             count_launch();
-        };
-        launch(-1, 1, 0);                                  // panel 0
-        for (int k = 0; k + 1 < nblk;) {
-            const int rem = nblk - 1 - k;                  // block rows of the trailing matrix after step k
-            if (pair_min > 0 && rem >= pair_min && k + 2 < nblk) {
-                launch(k, 1, 1);                           // thin: block row / column k + 1 take panel k, panel k + 1 factored and exchanged
-                launch(k, 2, 0);                           // the rest takes panels k and k + 1 in one visit, panel k + 2 on the way
-                k += 2;
-            } else {
-                launch(k, 1, 0);
-                k += 1;
-            }
         }
     } else {
     if (0 % P == rank) owner(0);
@@ -1197,6 +1232,27 @@ int lu_dist_factor_solve_p2p(Scene* s, double* rhs, double* x, cudaStream_t st) 
     LLS_CUDA_TRY(cudaMemcpyAsync(x, pr.xbuf[rank], sizeof(double) * (size_t)s->ld, cudaMemcpyDeviceToDevice, st));
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;
+}
+
+// ---- the schedule as data, for the CPU tests: no GPU is touched ---------------------------------------------------------------------
+int dist_debug_schedule(int nblk, int P, int rank, int pair_min, int* out, int max_launches) {
+    if (nblk < 1 || P < 1 || rank < 0 || rank >= P || nblk % P != 0) return -1;
+    const int nloc = nblk / P;
+    if (pair_min < 0) pair_min = dist_default_pair_min(P, pair_min == -1);        // -1: default with multicast, -2: default without
+    const int n = dist_schedule(nblk, P, rank, nloc, pair_min, nullptr, 0);
+    if (out == nullptr) return n;
+    std::vector<DistLaunch> plan((size_t)n);
+    dist_schedule(nblk, P, rank, nloc, pair_min, plan.data(), n);
+    for (int e = 0; e < n && e < max_launches; ++e) {
+        const DistLaunch& L = plan[(size_t)e];
+        int* o = out + 9 * e;
+        o[0] = L.k; o[1] = L.passes; o[2] = L.thin; o[3] = L.base; o[4] = L.rem; o[5] = L.lb0; o[6] = L.nloc; o[7] = L.own;
+        o[8] = (int)L.grid;
+    }
+    return n;
+}
+int dist_debug_role(int b, int own, int rem, int base, int lb0, int nloc, int thin, int* lb, int* bj) {
+    return dist_role(b, own, rem, base, lb0, nloc, thin, *lb, *bj);
 }
 
 }  // namespace lls
