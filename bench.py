@@ -80,7 +80,16 @@ def load_workload(name):
     return load(fixture)
 
 
+def swarm_solver(args):
+    """Solver settings of the swarm scene, read from its JSON input (the same dictionary in both arms)."""
+    from workloads import swarm_input
+    sp = swarm_input(8 if args.swarm_aircraft != 4 else 4, 1).get("solver", {})
+    return {"type": sp.get("type", "nonlinear"), "convergence": sp.get("convergence", 1e-10), "relaxation": sp.get("relaxation", 1.0),
+            "max_iterations": sp.get("max_iterations", 100)}
+
+
 def swarm_config(args, n, ld, solver):
+    ld = n      # the description of the workload does not depend on how many ranks pad the leading dimension
     return {"workload": "synthetic %d-aircraft swarm (examples/Swarm drone on the 8-column lattice of SURVEY.md section 8d, grid.N=%d per "
                         "wing segment), ONE scene of %d control points, nonlinear Newton solve; rows of V_ji / J partitioned over "
                         "the GPUs, distributed LU (BASELINE.json configs[3]-[4] family; strong scaling)" % (args.swarm_aircraft, args.swarm_grid, n),
@@ -243,7 +252,7 @@ def run_reference(args):
         iters = 13
         est, parts = swarm_port_estimate(n, iters, threads)
         value = 1.0 / est
-        solver = {"type": "nonlinear", "convergence": 1e-10, "relaxation": 1.0, "max_iterations": 100}
+        solver = swarm_solver(args)
         sample = ("the unmodified reference cannot hold this scene (about 0.66 kB of RSS per control-point pair = %.0f GB, BASELINE.md "
                   "section 2); oracle port (numpy/LAPACK restatement of scene.py:557-1117) timed on the N = 4,000 fixture with %d BLAS threads "
                   "(V_ji rows for 256 control points scaled to N, one linear assembly / residual / Jacobian / dense solve) and scaled "
@@ -432,8 +441,8 @@ def run_ours_swarm(args):
     lu_flops = n_fact * (2.0 / 3.0) * float(n) ** 3
     lu_tflops_per_gpu = lu_flops / (tm["lu"] * 1e-3) * 1e-12 / world if tm["lu"] > 0 else 0.0
     names = list(FM.keys())
-    solver = {"type": scene._solver_type, "convergence": scene._solver_convergence, "relaxation": scene._solver_relaxation,
-              "max_iterations": scene._max_solver_iterations}
+    solver = swarm_solver(args)
+    assert solver["type"] == scene._solver_type and solver["relaxation"] == scene._solver_relaxation
     value = args.steps / (dev_ms * 1e-3)
     e2e_value = args.steps / (wall_ms * 1e-3)
     h2d = scene._num_aircraft * 16 * 8
