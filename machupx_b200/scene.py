@@ -1330,7 +1330,24 @@ class Scene:
     def _out_of_scope(self, *args, **kwargs):
         raise NotImplementedError("plotting / CAD / simulator-model export is outside the lifting-line solve path this package implements")
 
-    display_wireframe = display_planform = export_stl = export_vtk = export_stp = export_dxf = out_gamma = _out_of_scope
+    display_wireframe = display_planform = export_stl = export_vtk = export_stp = export_dxf = _out_of_scope
+
+    def out_gamma(self, filename="gamma_dist.txt"):
+        """Writes the circulation distribution and the local velocities of the last solve to a text file in the reference's
+        layout (scene.py:3792-3827: ``i y gamma`` per control point, a header line, then ``y v_i V_i``); the two matplotlib figures
+        the reference opens afterwards are outside the solve path and are not produced."""
+        if not self._solved:
+            self.solve_forces()
+        y_locs = self._PC[:, 1]
+        v_i = np.asarray(self._v_i)
+        V_i = np.linalg.norm(v_i, axis=-1)
+        gamma = np.asarray(self._gamma)
+        with open(filename, "w") as handle:
+            for i in range(self._N):
+                print(i, y_locs[i], gamma[i], file=handle)
+            print("i  y  v_i  V_i", file=handle)
+            for i in range(self._N):
+                print(y_locs[i], v_i[i, :], V_i[i], file=handle)
 
     # ------------------------------------------------------------------------------------------------------
     # linearised model for the Pylot simulator: 59 solves of the hot path (scene.py:3521-3747)

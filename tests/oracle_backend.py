@@ -64,6 +64,7 @@ class OracleDeviceScene:
     def out(self):
         out = np.zeros((L.NO, self.n))
         out[L.O_GAMMA] = self._res["gamma"]
+        out[L.O_VI:L.O_VI + 3] = np.asarray(self._res["dist"]["v_i"]).T
         return out
 
 
