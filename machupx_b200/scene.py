@@ -198,6 +198,14 @@ class Scene:
     def add_aircraft(self, airplane_name, airplane_input, state={}, control_state={}):
         position = np.array(state.get("position", [0.0, 0.0, 0.0]))           # scene.py:287-301
         v_wind = self._get_wind(position)
+        # Re-adding a name REPLACES that aircraft (the reference's own tests do it, test_airfoil_interpolation.py:139-142).  The
+        # reference then counts the replaced aircraft's control points twice (scene.py:296-297) and carries zero rows; here the
+        # old aircraft is taken out of the counts first, so the scene stays solvable.
+        previous = self._airplanes.pop(airplane_name, None)
+        if previous is not None:
+            self._N -= previous.N
+            self._num_aircraft -= 1
+            self._device = self._device_revs = self._batch_device = self._part_device = None
         self._airplanes[airplane_name] = Airplane(airplane_name, airplane_input, self._unit_sys, self, init_state=state,
                                                   init_control_state=control_state, v_wind=v_wind)
         self._N += self._airplanes[airplane_name].N
