@@ -42,7 +42,7 @@ extern "C" {
 #define LLS_STATUS_SMALL_PIVOT 8
 #define LLS_STATUS_BITS 6 /* number of status bits defined below */
 #define LLS_STATUS_COMM 32 /* row-partitioned solve: a rank waited 30 s for a peer's data (a peer died or fell out of step) */
-#define LLS_STATUS_SECTION_BOUNDS 16 /* a poly_fit airfoil was evaluated outside the limits of its fit (airfoil_db: PolyFitBoundsError) */
+#define LLS_STATUS_SECTION_BOUNDS 16 /* a poly_fit airfoil was evaluated outside the limits of its fit, or a database airfoil outside its table (airfoil_db: DatabaseBoundsError) */
 
 /* ---- solver flags (reference: scene.py:82-87) ------------------------------------------ */
 #define LLS_FLAG_SWEPT_SECTIONS 1
@@ -50,6 +50,7 @@ extern "C" {
 #define LLS_FLAG_IN_PLANE 4
 #define LLS_FLAG_MATCH_MACHUP_PRO 8
 #define LLS_FLAG_CONSTRAIN_VORTEX_SHEET 16 /* trailing directions projected off the body z axis and renormalised (scene.py:595-611) */
+#define LLS_FLAG_DATABASE_AIRFOILS 32 /* at least one airfoil block is a table look-up (LLS_AF_TYPE == 2): the section-model kernels with the table walk are launched */
 #define LLS_FLAG_DEFAULT (LLS_FLAG_SWEPT_SECTIONS | LLS_FLAG_TOTAL_VELOCITY | LLS_FLAG_IN_PLANE)
 
 /* ---- per-control-point double table fields --------------------------------------------- */
@@ -103,7 +104,7 @@ enum lls_ifield {
 
 /* ---- airfoil parameter block (one per airfoil id), doubles ------------------------------ */
 enum lls_airfoil_field {
-    LLS_AF_TYPE = 0, /* 0 = linear (airfoil_db "linear") ; 1 = poly_fit                        */
+    LLS_AF_TYPE = 0, /* 0 = linear (airfoil_db "linear") ; 1 = poly_fit ; 2 = database (needs LLS_FLAG_DATABASE_AIRFOILS) */
     LLS_AF_AL0 = 1,
     LLS_AF_CLA = 2,
     LLS_AF_CML0 = 3,
@@ -112,7 +113,7 @@ enum lls_airfoil_field {
     LLS_AF_CD1 = 6,
     LLS_AF_CD2 = 7,
     LLS_AF_CLMAX = 8,
-    /* poly_fit airfoils (LLS_AF_TYPE == 1) reuse the block: */
+    /* poly_fit and database airfoils (LLS_AF_TYPE == 1, 2) reuse the block: */
     LLS_AF_POLY_OFF = 1,  /* offset (in doubles, from the start of the airfoil buffer) of this airfoil's record in the pool      */
     LLS_AF_POLY_NDOF = 2, /* number of independent variables V (<= 5)                                                       */
     LLS_AF_POLY_DOF0 = 3, /* V kind codes: 0 alpha, 1 Rey, 2 Mach, 3 trailing_flap_deflection [rad], 4 trailing_flap_fraction */
@@ -121,7 +122,18 @@ enum lls_airfoil_field {
 /* Pool record of a poly_fit airfoil (doubles), after the n_airfoils parameter blocks of the airfoil buffer:
  *   limits: V x (lower, upper); then for CL, CD, Cm in this order: ncoef, V degrees, ncoef coefficients
  * with the coefficient index running like airfoil_db's fits: exponent tuple row-major, LAST variable fastest
- * (reference machupX/poly_fits.py:398-431 compose_j). */
+ * (reference machupX/poly_fits.py:398-431 compose_j).
+ *
+ * Pool record of a database airfoil (airfoil_db "database": CL, CD, Cm tabulated over V of the five variables, interpolated
+ * barycentrically on the Delaunay triangulation of the P data points in variables scaled to [0, 1]; for V = 1 the S = P - 1
+ * simplices are the intervals between consecutive points).  The caller triangulates (scipy.spatial.Delaunay on the scaled
+ * points is what airfoil_db's griddata call does); the library only walks the table:
+ *   P, S; limits: V x (lower, span = upper - lower); values: P x (CL, CD, Cm);
+ *   simplices: S x [V + 1 vertex ids (as doubles) | V x V row-major map Tinv | V origin r (= the last vertex, scaled)],
+ * barycentric coordinates of a scaled point x: c[0..V) = Tinv (x - r), c[V] = 1 - sum c; a flat simplex carries NaN in Tinv.
+ * CLa / CLRe / CLM: central differences of the CL table with steps 0.001 rad / 1000 / 0.05, samples kept inside the limits;
+ * aL0: root of the CL table in alpha (secant from 0 and 0.01).  A point outside the table sets LLS_STATUS_SECTION_BOUNDS and
+ * extrapolates from the closest simplex.  Pinned by the reference's golden, tests/test_database_airfoils.py. */
 
 /* ---- per-aircraft state block, doubles --------------------------------------------------- */
 enum lls_aircraft_field {

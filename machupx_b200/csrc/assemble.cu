@@ -111,6 +111,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // everything of a residual row after v_i: section lift (scene.py:732-791), R_i (scene.py:723), the row vectors of the Jacobian.
 // Per-case pointers already applied by the caller.
+template <bool DB>
 __device__ __forceinline__ void residual_row_tail(int i, const Vec3& vi, int ld, int flags, const double* __restrict__ tab,
                                                   const int32_t* __restrict__ itab, const double* __restrict__ af, double* __restrict__ W,
                                                   double* __restrict__ out, double* __restrict__ partial, int* __restrict__ status_case) {
@@ -131,9 +132,9 @@ __device__ __forceinline__ void residual_row_tail(int i, const Vec3& vi, int ld,
     const double alpha = atan2(vn, va);
     const SectionParams sp = load_section(tab, itab, af, ld, i);
     bool oob = false;
-    const double CLa = section_CLa(sp, alpha, Re, Mach);                          // scene.py:765-768
-    double CL = section_CL(sp, alpha, Re, Mach, oob);
-    const double CLRe = section_CLRe(sp, alpha, Re, Mach), CLM = section_CLM(sp, alpha, Re, Mach);
+    const double CLa = section_CLa<DB>(sp, alpha, Re, Mach);                      // scene.py:765-768
+    double CL = section_CL<DB>(sp, alpha, Re, Mach, oob);
+    const double CLRe = section_CLRe<DB>(sp, alpha, Re, Mach), CLM = section_CLM<DB>(sp, alpha, Re, Mach);
     if (oob) atomicOr(status_case, LLS_STATUS_SECTION_BOUNDS);
     const double dS = tab[(size_t)LLS_F_DS * ld + i];
     const double Vinf = W[(size_t)W_VINF_MAG * ld + i];
@@ -172,7 +173,7 @@ __device__ __forceinline__ void residual_row_tail(int i, const Vec3& vi, int ld,
 // THREADS threads share a row; ROWS rows per CTA.  ROWS > 1 needs THREADS == 32 (one warp per row, reduction by shuffles only): the
 // shape for the small scenes of large batches, where a row is shorter than a CTA and the scalar tail of the row (section lift,
 // Jacobian row vectors) is what there is to hide.
-template <int THREADS, int ROWS = 1, bool TAIL = true>
+template <int THREADS, int ROWS = 1, bool TAIL = true, bool DB = false>
 __global__ void __launch_bounds__(THREADS * ROWS) residual_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                            const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                            const double* __restrict__ V, double* __restrict__ W,
@@ -227,11 +228,12 @@ __global__ void __launch_bounds__(THREADS * ROWS) residual_kernel(int n, int ld,
         st3(out, ld, LLS_O_VI, i, vi);
         return;
     }
-    residual_row_tail(i, vi, ld, flags, tab, itab, af, W, out, partial, case_work_ptr(status, cs.work));
+    residual_row_tail<DB>(i, vi, ld, flags, tab, itab, af, W, out, partial, case_work_ptr(status, cs.work));
 }
 
 // The tail of every row as one THREAD per row (batches of small scenes): all table reads are coalesced along i and no lane idles,
 // where the fused kernel leaves the whole tail to one lane of the row's warp.
+template <bool DB>
 __global__ void __launch_bounds__(128) residual_tail_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                             const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                             double* __restrict__ W, double* __restrict__ out, double* __restrict__ partial,
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(128) residual_tail_kernel(int n, int ld, int f
     partial = case_work_ptr(partial, cs.work);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    residual_row_tail(i, ld3(out, ld, LLS_O_VI, i), ld, flags, tab, itab, af, W, out, partial, case_work_ptr(status, cs.work));
+    residual_row_tail<DB>(i, ld3(out, ld, LLS_O_VI, i), ld, flags, tab, itab, af, W, out, partial, case_work_ptr(status, cs.work));
 }
 
 // deterministic sum of partial[0..n) -> scalars[slot]
@@ -296,19 +298,22 @@ int launch_assemble_linear(Scene* s, cudaStream_t st) {
 
 int launch_residual(Scene* s, int vel_only, cudaStream_t st, bool masked) {
     const int rows = s->cs.P == 1 ? s->n : s->n_loc_blocks * 64;
+    const bool db = (s->flags & LLS_FLAG_DATABASE_AIRFOILS) != 0;   // section model with table look-ups: the <DB = true> kernels
     if (s->ld <= 512 && s->ncases > 1) {
         // small scenes in large batches: one warp per row, 8 rows per CTA
         // ... and the tail of the rows as a kernel of its own, one thread per row
         residual_kernel<32, 8, false><<<dim3((rows + 7) / 8, 1, s->ncases), 256, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W,
                                                                                        s->out, s->partial, vel_only, s->status, strides(s, masked));
         if (!vel_only) {
-            residual_tail_kernel<<<dim3((s->n + 127) / 128, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out,
-                                                                                      s->partial, s->status, strides(s, masked));
+            auto tail = db ? residual_tail_kernel<true> : residual_tail_kernel<false>;
+            tail<<<dim3((s->n + 127) / 128, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out, s->partial,
+                                                                      s->status, strides(s, masked));
             count_launch();
         }
     } else {
-        residual_kernel<128><<<dim3(rows, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial,
-                                                                      vel_only, s->status, strides(s, masked));
+        auto fused = db ? residual_kernel<128, 1, true, true> : residual_kernel<128, 1, true, false>;
+        fused<<<dim3(rows, 1, s->ncases), 128, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->V, s->W, s->out, s->partial, vel_only,
+                                                        s->status, strides(s, masked));
     }
     count_launch();
     if (!vel_only) {

@@ -6,6 +6,7 @@
 
 namespace lls {
 
+template <bool DB>
 __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                         const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                         const double* __restrict__ ac, double* __restrict__ W,
@@ -75,9 +76,9 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
     const double alpha_inf = atan2(dot(vir, un), dot(vir, ua));                  // scene.py:649-651
     SectionParams sp = load_section(tab, itab, af, ld, i);
     bool oob = false;
-    const double CLa = section_CLa(sp, alpha_inf, Re, Mach);                     // scene.py:659-661
-    double CL = section_CL(sp, alpha_inf, Re, Mach, oob);
-    const double aL0 = section_aL0(sp, Re, Mach);
+    const double CLa = section_CLa<DB>(sp, alpha_inf, Re, Mach);                 // scene.py:659-661
+    double CL = section_CL<DB>(sp, alpha_inf, Re, Mach, oob);
+    const double aL0 = section_aL0<DB>(sp, Re, Mach);
     if (oob) atomicOr(status, LLS_STATUS_SECTION_BOUNDS);
     if (flags & LLS_FLAG_SWEPT_SECTIONS) {                                       // scene.py:665-666, 797
         CL += CLa * (aL0 - aL0 * tab[(size_t)LLS_F_CSWI * ld + i]);
@@ -93,8 +94,9 @@ int launch_flow_state(Scene* s, cudaStream_t st) {
     // bounds), and a reset from inside the kernel could wipe a bit another block had already set
     if (s->ncases > 1) LLS_CUDA_TRY(cudaMemset2DAsync(s->status, s->cs.work, 0, sizeof(int), (size_t)s->ncases, st));
     else LLS_CUDA_TRY(cudaMemsetAsync(s->status, 0, sizeof(int), st));
-    flow_state_kernel<<<dim3(grid, 1, s->ncases), block, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->ac, s->W, s->out, s->status,
-                                                                  strides(s, false));
+    auto kernel = (s->flags & LLS_FLAG_DATABASE_AIRFOILS) ? flow_state_kernel<true> : flow_state_kernel<false>;
+    kernel<<<dim3(grid, 1, s->ncases), block, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->ac, s->W, s->out, s->status,
+                                                       strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;

@@ -29,6 +29,7 @@ __device__ __forceinline__ int lower_bound_seg(const int32_t* __restrict__ seg, 
 
 constexpr int INT_THREADS = 128;
 
+template <bool DB>
 __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, int flags, const double* __restrict__ tab,
                                                                 const int32_t* __restrict__ itab, const double* __restrict__ af,
                                                                 const double* __restrict__ W, double* __restrict__ out,
@@ -84,8 +85,8 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
         }
         const SectionParams sp = load_section(tab, itab, af, ld, i);
         bool oob = false;
-        const double CD = section_CD(sp, alpha_unswept, Re_unswept, Mach, oob);      // scene.py:1014-1017
-        double Cm = section_Cm(sp, alpha, Re, Mach, oob);                            // scene.py:1020
+        const double CD = section_CD<DB>(sp, alpha_unswept, Re_unswept, Mach, oob);  // scene.py:1014-1017
+        double Cm = section_Cm<DB>(sp, alpha, Re, Mach, oob);                        // scene.py:1020
         if (oob) atomicOr(status, LLS_STATUS_SECTION_BOUNDS);
         if (swept) Cm *= cswi;                                                       // scene.py:1026
         const Vec3 dM_section = ((in_plane ? redim_ip : redim_full) * cbar * Cm) * us;   // scene.py:1029-1032
@@ -129,8 +130,9 @@ __global__ void __launch_bounds__(INT_THREADS) integrate_kernel(int n, int ld, i
 }
 
 int launch_integrate(Scene* s, double* d_seg_fm, cudaStream_t st) {
-    integrate_kernel<<<dim3(s->n_seg, 1, s->ncases), INT_THREADS, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out, d_seg_fm,
-                                                                           s->status, strides(s, false));
+    auto kernel = (s->flags & LLS_FLAG_DATABASE_AIRFOILS) ? integrate_kernel<true> : integrate_kernel<false>;
+    kernel<<<dim3(s->n_seg, 1, s->ncases), INT_THREADS, 0, st>>>(s->n, s->ld, s->flags, s->tab, s->itab, s->af, s->W, s->out, d_seg_fm, s->status,
+                                                                 strides(s, false));
     count_launch();
     LLS_CUDA_TRY(cudaGetLastError());
     return LLS_OK;

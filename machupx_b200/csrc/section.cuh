@@ -1,9 +1,10 @@
-// Device section model: the airfoil_db "linear" and "poly_fit" airfoils (third-party dependency of the reference,
+// Device section model: the airfoil_db "linear", "poly_fit" and "database" airfoils (third-party dependency of the reference,
 // airfoil_db>=1.4.3, setup.py:13), evaluated per control point inside the Newton loop.
 // Two bracketing airfoils blended linearly in span (wing_segment.py:1062-1072, 1104-1124).
 // Host mirror: machupx_b200/airfoil.py; oracle mirror: oracle/lls_oracle.py section_*().
 #pragma once
 #include "lls_internal.h"
+#include "db_airfoil.cuh"
 
 namespace lls {
 
@@ -49,7 +50,24 @@ struct PolyPoint {
 };
 enum { POLY_CL = 0, POLY_CD = 1, POLY_CM = 2 };
 
-__device__ __forceinline__ bool is_poly(const double* blk) { return blk[LLS_AF_TYPE] > 0.5; }
+__device__ __forceinline__ bool is_poly(const double* blk) { return blk[LLS_AF_TYPE] > 0.5; }   // tested after is_db() where both occur
+__device__ __forceinline__ bool is_db(const double* blk) { return blk[LLS_AF_TYPE] > 1.5; }
+
+// ---- database airfoils (db_airfoil.cuh).  The block of a database airfoil uses the poly_fit fields (pool offset, V, variable
+// codes).  Every kernel that evaluates the section model exists twice: the <DB = true> instantiations, launched for scenes with
+// LLS_FLAG_DATABASE_AIRFOILS, carry the table walk (one out-of-line function); the <DB = false> ones are the kernels as they
+// were, instruction for instruction, so the analytic models pay neither registers nor code for it.
+static __device__ __noinline__ DbResult db_section(const double* base, const double* blk, double alpha, double Re, double Mach,
+                                            double defl, double cf, int what) {
+    return db_evaluate(base + (size_t)blk[LLS_AF_POLY_OFF], (int)blk[LLS_AF_POLY_NDOF], blk + LLS_AF_POLY_DOF0, alpha, Re, Mach,
+                       defl, cf, what);
+}
+__device__ __forceinline__ double db_value(const SectionParams& p, const double* blk, double alpha, double Re, double Mach, int what,
+                                           bool& oob) {
+    const DbResult r = db_section(p.base, blk, alpha, Re, Mach, p.defl, p.cf, what);
+    oob |= r.oob != 0;
+    return r.value;
+}
 
 __device__ inline PolyPoint poly_point(const SectionParams& p, const double* blk, double alpha, double Re, double Mach) {
     PolyPoint pt;
@@ -101,7 +119,9 @@ __device__ inline double poly_eval(const SectionParams& p, const double* blk, co
 }
 
 // one airfoil: CL, its alpha / Rey / Mach derivatives
+template <bool DB>
 __device__ inline double af_CL(const SectionParams& p, const double* blk, double alpha, double Re, double Mach, bool& oob) {
+    if (DB && is_db(blk)) return db_value(p, blk, alpha, Re, Mach, DB_CL, oob);
     if (is_poly(blk)) {
         const PolyPoint pt = poly_point(p, blk, alpha, Re, Mach);
         oob |= pt.out_of_bounds;
@@ -109,11 +129,21 @@ __device__ inline double af_CL(const SectionParams& p, const double* blk, double
     }
     return clipd(blk[LLS_AF_CLA] * (alpha - blk[LLS_AF_AL0] + p.flap_da), blk[LLS_AF_CLMAX]);
 }
+template <bool DB>
 __device__ inline double af_CL_d(const SectionParams& p, const double* blk, double alpha, double Re, double Mach, int dkind) {
+    if (DB && is_db(blk)) {
+        bool ignored = false;
+        return db_value(p, blk, alpha, Re, Mach, DB_CLA + dkind, ignored);
+    }
     if (is_poly(blk)) return poly_eval(p, blk, poly_point(p, blk, alpha, Re, Mach), POLY_CL, dkind);
     return dkind == 0 ? blk[LLS_AF_CLA] : 0.0;
 }
+template <bool DB>
 __device__ inline double af_aL0(const SectionParams& p, const double* blk, double Re, double Mach) {
+    if (DB && is_db(blk)) {
+        bool ignored = false;
+        return db_value(p, blk, 0.0, Re, Mach, DB_AL0, ignored);
+    }
     if (!is_poly(blk)) return blk[LLS_AF_AL0] - p.flap_da;
     double a0 = 0.0;
     for (int it = 0; it < 30; ++it) {
@@ -127,24 +157,31 @@ __device__ inline double af_aL0(const SectionParams& p, const double* blk, doubl
 }
 
 // CL = clip(CLa (alpha - aL0 + delta eps), +-CL_max)   (linear)   |   polynomial (poly_fit)
+template <bool DB>
 __device__ __forceinline__ double section_CL(const SectionParams& p, double alpha, double Re, double Mach, bool& oob) {
-    return blendd(p.wb, af_CL(p, p.a, alpha, Re, Mach, oob), af_CL(p, p.b, alpha, Re, Mach, oob));
+    return blendd(p.wb, af_CL<DB>(p, p.a, alpha, Re, Mach, oob), af_CL<DB>(p, p.b, alpha, Re, Mach, oob));
 }
+template <bool DB>
 __device__ __forceinline__ double section_CLa(const SectionParams& p, double alpha, double Re, double Mach) {
-    return blendd(p.wb, af_CL_d(p, p.a, alpha, Re, Mach, 0), af_CL_d(p, p.b, alpha, Re, Mach, 0));
+    return blendd(p.wb, af_CL_d<DB>(p, p.a, alpha, Re, Mach, 0), af_CL_d<DB>(p, p.b, alpha, Re, Mach, 0));
 }
+template <bool DB>
 __device__ __forceinline__ double section_CLRe(const SectionParams& p, double alpha, double Re, double Mach) {
-    return blendd(p.wb, af_CL_d(p, p.a, alpha, Re, Mach, 1), af_CL_d(p, p.b, alpha, Re, Mach, 1));
+    return blendd(p.wb, af_CL_d<DB>(p, p.a, alpha, Re, Mach, 1), af_CL_d<DB>(p, p.b, alpha, Re, Mach, 1));
 }
+template <bool DB>
 __device__ __forceinline__ double section_CLM(const SectionParams& p, double alpha, double Re, double Mach) {
-    return blendd(p.wb, af_CL_d(p, p.a, alpha, Re, Mach, 2), af_CL_d(p, p.b, alpha, Re, Mach, 2));
+    return blendd(p.wb, af_CL_d<DB>(p, p.a, alpha, Re, Mach, 2), af_CL_d<DB>(p, p.b, alpha, Re, Mach, 2));
 }
+template <bool DB>
 __device__ __forceinline__ double section_aL0(const SectionParams& p, double Re, double Mach) {
-    return blendd(p.wb, af_aL0(p, p.a, Re, Mach), af_aL0(p, p.b, Re, Mach));
+    return blendd(p.wb, af_aL0<DB>(p, p.a, Re, Mach), af_aL0<DB>(p, p.b, Re, Mach));
 }
 
 // CD = CD0 + CD1 CL + CD2 CL^2 (CL without flap) + 0.002 |delta| 180/pi   (linear)
+template <bool DB>
 __device__ inline double af_CD(const SectionParams& p, const double* blk, double alpha, double Re, double Mach, bool& oob) {
+    if (DB && is_db(blk)) return db_value(p, blk, alpha, Re, Mach, DB_CD, oob);
     if (is_poly(blk)) {
         const PolyPoint pt = poly_point(p, blk, alpha, Re, Mach);
         oob |= pt.out_of_bounds;
@@ -153,12 +190,15 @@ __device__ inline double af_CD(const SectionParams& p, const double* blk, double
     const double cl = clipd(blk[LLS_AF_CLA] * (alpha - blk[LLS_AF_AL0]), blk[LLS_AF_CLMAX]);
     return blk[LLS_AF_CD0] + blk[LLS_AF_CD1] * cl + blk[LLS_AF_CD2] * cl * cl + p.flap_dcd;
 }
+template <bool DB>
 __device__ __forceinline__ double section_CD(const SectionParams& p, double alpha, double Re, double Mach, bool& oob) {
-    return blendd(p.wb, af_CD(p, p.a, alpha, Re, Mach, oob), af_CD(p, p.b, alpha, Re, Mach, oob));
+    return blendd(p.wb, af_CD<DB>(p, p.a, alpha, Re, Mach, oob), af_CD<DB>(p, p.b, alpha, Re, Mach, oob));
 }
 
 // Cm = Cma (alpha - aL0) + CmL0 + delta dCm   (linear)
+template <bool DB>
 __device__ inline double af_Cm(const SectionParams& p, const double* blk, double alpha, double Re, double Mach, bool& oob) {
+    if (DB && is_db(blk)) return db_value(p, blk, alpha, Re, Mach, DB_CM, oob);
     if (is_poly(blk)) {
         const PolyPoint pt = poly_point(p, blk, alpha, Re, Mach);
         oob |= pt.out_of_bounds;
@@ -166,8 +206,9 @@ __device__ inline double af_Cm(const SectionParams& p, const double* blk, double
     }
     return blk[LLS_AF_CMA] * (alpha - blk[LLS_AF_AL0]) + blk[LLS_AF_CML0] + p.flap_dcm;
 }
+template <bool DB>
 __device__ __forceinline__ double section_Cm(const SectionParams& p, double alpha, double Re, double Mach, bool& oob) {
-    return blendd(p.wb, af_Cm(p, p.a, alpha, Re, Mach, oob), af_Cm(p, p.b, alpha, Re, Mach, oob));
+    return blendd(p.wb, af_Cm<DB>(p, p.a, alpha, Re, Mach, oob), af_Cm<DB>(p, p.b, alpha, Re, Mach, oob));
 }
 
 struct Vec3 {

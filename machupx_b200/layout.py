@@ -19,7 +19,7 @@ NI = 7
 
 # airfoil block (enum lls_airfoil_field)
 AF_TYPE, AF_AL0, AF_CLA, AF_CML0, AF_CMA, AF_CD0, AF_CD1, AF_CD2, AF_CLMAX = 0, 1, 2, 3, 4, 5, 6, 7, 8
-AF_POLY_OFF, AF_POLY_NDOF, AF_POLY_DOF0 = 1, 2, 3   # poly_fit airfoils (AF_TYPE == 1) reuse the block
+AF_POLY_OFF, AF_POLY_NDOF, AF_POLY_DOF0 = 1, 2, 3   # poly_fit (AF_TYPE == 1) and database (AF_TYPE == 2) airfoils reuse the block
 AF_STRIDE = 16
 POLY_DOF_KINDS = ("alpha", "Rey", "Mach", "trailing_flap_deflection", "trailing_flap_fraction")
 
@@ -35,6 +35,7 @@ NO = 33
 
 # solver flags
 FLAG_SWEPT_SECTIONS, FLAG_TOTAL_VELOCITY, FLAG_IN_PLANE, FLAG_MATCH_MACHUP_PRO, FLAG_CONSTRAIN_VORTEX_SHEET = 1, 2, 4, 8, 16
+FLAG_DATABASE_AIRFOILS = 32   # some airfoil block is a table look-up (AF_TYPE == 2)
 FLAG_DEFAULT = FLAG_SWEPT_SECTIONS | FLAG_TOTAL_VELOCITY | FLAG_IN_PLANE
 
 # status bits

@@ -15,8 +15,8 @@ exactly those private methods with calls into liblls (include/lls.h) through ``D
     _integrate_forces_and_moments      scene.py:927     lls_integrate + forces.assemble_fm (O(#segments) host)
 
 There is no CPU fallback: without a CUDA device (or without liblls.so) ``solve_forces`` raises.  Inputs the device
-section model cannot evaluate ("database"/callable airfoils, the scipy_fsolve solver) raise NotImplementedError
-before anything is launched.
+section model cannot evaluate (callable airfoils, the scipy_fsolve solver) raise NotImplementedError before anything
+is launched; "linear", "poly_fit" and "database" airfoils are evaluated on the device.
 """
 import copy
 import json
@@ -47,7 +47,7 @@ _SMALL_PIVOT_TEXT = ("The unpivoted LU factorisation of the lifting-line system 
 _NAN_TEXT = ("The lifting-line solve produced NaN (a zero or NaN pivot in the LU factorisation, or a NaN residual); the reference "
              "propagates NaN silently in this situation (docs/source/common_issues.md).")
 
-_BOUNDS_TEXT = "A poly_fit airfoil was evaluated outside the limits of its fit."
+_BOUNDS_TEXT = "A poly_fit airfoil was evaluated outside the limits of its fit, or a database airfoil outside its table."
 
 _FRAME_KEYS = {"body": ("Cx", "Cy", "Cz", "Cl", "Cm", "Cn"),
                "stab": ("Cx_s", "Cy_s", "Cz_s", "Cl_s", "Cm_s", "Cn_s"),

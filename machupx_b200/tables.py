@@ -107,7 +107,7 @@ def build_tables(scene):
             airfoil_ids[key] = len(airfoil_blocks)
             airfoil_blocks.append(airfoil_param_block(obj))
             airfoil_pools.append(np.asarray(obj.lls_pool(), dtype=np.float64) if hasattr(obj, "lls_pool") and
-                                 getattr(obj, "_type", "linear") == "poly_fit" else None)
+                                 getattr(obj, "_type", "linear") in ("poly_fit", "database") else None)
         return airfoil_ids[key]
 
     swept = bool(scene._use_swept_sections)
@@ -206,7 +206,7 @@ def build_tables(scene):
     tab[L.F_SOS, :n] = np.broadcast_to(np.asarray(scene._a, dtype=float), (n,))
     tab[L.F_VWIND:L.F_VWIND + 3, :n] = np.asarray(scene._v_wind, dtype=float).reshape(n, 3).T
 
-    # airfoil buffer: one parameter block per airfoil, then the records of the poly_fit airfoils (offsets patched into their
+    # airfoil buffer: one parameter block per airfoil, then the records of the poly_fit / database airfoils (offsets patched into their
     # blocks), padded to a whole number of blocks so the buffer still reshapes to (-1, AF_STRIDE)
     blocks = np.asarray(airfoil_blocks, dtype=np.float64).reshape(-1, L.AF_STRIDE)
     pool, offset = [], blocks.size
@@ -217,11 +217,14 @@ def build_tables(scene):
             offset += rec.size
     flat = np.concatenate([blocks.ravel()] + pool) if pool else blocks.ravel()
     flat = np.concatenate((flat, np.zeros((-flat.size) % L.AF_STRIDE)))
+    flags = solver_flags(scene)
+    if (blocks[:, L.AF_TYPE] > 1.5).any():
+        flags |= L.FLAG_DATABASE_AIRFOILS
     return {
         "tab": tab, "itab": itab, "airfoils": flat.reshape(-1, L.AF_STRIDE), "n_airfoils": blocks.shape[0],
         "n": n, "ld": ld, "n_aircraft": len(airplanes), "n_segments": seg_counter,
         "segment_names": seg_names, "segment_slices": seg_slices, "aircraft_slices": ac_slices,
-        "flags": solver_flags(scene),
+        "flags": flags,
     }
 
 

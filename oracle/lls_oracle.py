@@ -236,14 +236,104 @@ def _poly_one(T, a, mask, alpha, Re, M, which, dkind):
     return out
 
 
+# database airfoils (airfoil_db "database" type; third party).  Restated from its behaviour: barycentric interpolation on the
+# Delaunay triangulation of the data points in variables scaled to [0, 1] (scipy griddata, method "linear"), CLa / CLRe / CLM as
+# central differences of that interpolant with steps 0.001 / 1000 / 0.05, aL0 as its root in alpha.  PINNED by the reference's
+# golden of test/scene_tests/test_solve_forces.py:453-494 (tests/test_database_airfoils.py).  The triangulation itself is an
+# INPUT here (the pool record built by machupx_b200/airfoil.py with scipy, layout in include/lls.h).
+DB_EPS = 1e-12
+DB_STEP = {0: 0.001, 1: 1000.0, 2: 0.05}
+
+
+def _db_record(T, a):
+    flat = T.af.ravel()
+    blk = T.af[a]
+    V = int(blk[L.AF_POLY_NDOF])
+    kinds = [int(blk[L.AF_POLY_DOF0 + v]) for v in range(V)]
+    off = int(blk[L.AF_POLY_OFF])
+    P, S = int(flat[off]), int(flat[off + 1])
+    pos = off + 2
+    lim = flat[pos:pos + 2 * V].reshape(V, 2)
+    pos += 2 * V
+    vals = flat[pos:pos + 3 * P].reshape(P, 3)
+    pos += 3 * P
+    w = V + 1 + V * V + V
+    simp = flat[pos:pos + S * w].reshape(S, w)
+    return kinds, lim, vals, simp[:, :V + 1].astype(np.int64), simp[:, V + 1:V + 1 + V * V].reshape(S, V, V), simp[:, V + 1 + V * V:]
+
+
+def _db_eval(rec, X, which):
+    """Interpolated coefficient `which` at the raw points X (n, V); points outside the table extrapolate from the simplex whose
+    smallest barycentric coordinate is largest."""
+    kinds, lim, vals, verts, Tinv, r = rec
+    xn = (X - lim[:, 0]) / lim[:, 1]
+    out = np.zeros(len(xn))
+    for q in range(len(xn)):
+        c = np.einsum("sij,sj->si", Tinv, xn[q] - r)
+        c = np.concatenate((c, 1.0 - c.sum(axis=1, keepdims=True)), axis=1)
+        cmin = np.where(np.isnan(c).any(axis=1), -np.inf, c.min(axis=1))
+        inside = np.nonzero(cmin >= -DB_EPS)[0]
+        s = inside[0] if inside.size else int(np.argmax(cmin))
+        out[q] = np.dot(c[s], vals[verts[s], which])
+    return out
+
+
+def _db_points(T, rec, mask, alpha, Re, M):
+    cols = {0: alpha, 1: Re, 2: M, 3: T.FLAP_DEFL, 4: T.FLAP_CF}
+    return np.stack([np.broadcast_to(cols[k], (T.n,))[mask] for k in rec[0]], axis=1).astype(float)
+
+
+def _db_one(T, a, mask, alpha, Re, M, which, dkind):
+    rec = _db_record(T, a)
+    X = _db_points(T, rec, mask, alpha, Re, M)
+    if dkind is None:
+        return _db_eval(rec, X, which)
+    if dkind not in rec[0]:
+        return np.zeros(mask.sum())
+    v = rec[0].index(dkind)
+    lo, hi = rec[1][v, 0], rec[1][v, 0] + rec[1][v, 1]
+    x = X[:, v]
+    up = np.minimum(x + DB_STEP[dkind], np.maximum(hi, x)) - x           # samples stay inside the table's limits
+    dn = np.maximum(x - DB_STEP[dkind], np.minimum(lo, x)) - x
+    Xu, Xd = X.copy(), X.copy()
+    Xu[:, v] += up
+    Xd[:, v] += dn
+    return (_db_eval(rec, Xu, which) - _db_eval(rec, Xd, which)) / (up - dn)
+
+
+def _db_aL0(T, a, mask, Re, M):
+    rec = _db_record(T, a)
+    m = int(mask.sum())
+    if 0 not in rec[0]:
+        return np.zeros(m)
+    def CL(al):
+        alpha = np.zeros(T.n)
+        alpha[mask] = al
+        return _db_eval(rec, _db_points(T, rec, mask, alpha, Re, M), 0)
+    a0, a1 = np.zeros(m), np.full(m, 0.01)
+    f0, f1 = CL(a0), CL(a1)
+    for _ in range(50):                                                   # secant, exact on one linear piece
+        active = np.abs(a1 - a0) > 1e-10
+        if not active.any():
+            break
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a2 = np.where(active, a1 - f1 * (a0 - a1) / (f0 - f1), a1)
+        f2 = CL(a2)
+        a0, f0, a1, f1 = a1, f1, a2, f2
+    return a1
+
+
 def _per_airfoil(T, ids, alpha, Re, M, linear_fn, which, dkind=None):
-    """Evaluates one bracketing airfoil per control point: linear_fn(ids) for linear airfoils, the polynomial otherwise."""
+    """Evaluates one bracketing airfoil per control point: linear_fn(ids) for linear airfoils, the polynomial or the table
+    otherwise."""
     out = linear_fn(ids)
     for a in np.unique(ids):
-        if T.af[a, L.AF_TYPE] > 0.5:
+        kind = T.af[a, L.AF_TYPE]
+        if kind > 0.5:
             mask = ids == a
             out = np.array(out, dtype=float)
-            out[mask] = _poly_one(T, a, mask, alpha, Re, M, which, dkind)
+            one = _db_one if kind > 1.5 else _poly_one
+            out[mask] = one(T, a, mask, alpha, Re, M, which, dkind)
     return out
 
 
@@ -287,7 +377,11 @@ def section_aL0(T, Re=None, M=None):
     def one(ids):
         out = _af(T, ids, L.AF_AL0) - T.FLAP_DA
         for a in np.unique(ids):
-            if T.af[a, L.AF_TYPE] > 0.5:            # root of the CL fit in alpha by Newton's method from alpha = 0
+            if T.af[a, L.AF_TYPE] > 1.5:            # database airfoil: root of the table in alpha
+                mask = ids == a
+                out = np.array(out, dtype=float)
+                out[mask] = _db_aL0(T, a, mask, Re, M)
+            elif T.af[a, L.AF_TYPE] > 0.5:          # root of the CL fit in alpha by Newton's method from alpha = 0
                 mask = ids == a
                 a0 = np.zeros(T.n)
                 for _ in range(30):

