@@ -36,9 +36,12 @@ class AircraftFrame:
         u_side = np.cross(u_lift, u_inf)                                                          # scene.py:1091-1093
         u_side = u_side / np.linalg.norm(u_side)
         self.to_wind = np.array([u_inf, u_side, u_lift])
-        self.nd_force = 2.0 / (float(rho_at_origin) * self.V_inf * self.V_inf * S_w)              # scene.py:1097-1099
-        self.nd_lat = self.nd_force / l_ref_lat
-        self.nd_lon = self.nd_force / l_ref_lon
+        # numpy scalars, as in the reference: a zero reference length (a main wing that exists on the left side only,
+        # airplane.py:883-892) gives infinite / NaN moment coefficients there, not an exception
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.nd_force = np.float64(2.0) / (np.float64(rho_at_origin) * self.V_inf * self.V_inf * np.float64(S_w))   # scene.py:1097-1099
+            self.nd_lat = self.nd_force / np.float64(l_ref_lat)
+            self.nd_lon = self.nd_force / np.float64(l_ref_lon)
 
 
 def frames_from_scene(scene):

@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Differential fuzzer: random MachUpX inputs through the UNMODIFIED reference and through machupx_b200's host mirror
+(TEST INFRASTRUCTURE; runs in the build container only, where /root/reference exists).
+
+    python oracle/fuzz_host_mirror.py [--cases 200] [--seed 0] [--solve-every 4] [--keep tests/golden/fuzz_cases.json]
+
+For every generated scene (1-2 aircraft; 1-4 wing definitions with every documented way of giving span-wise distributions,
+connections, grids, control surfaces, units; random flight and control state; random solver flags) it compares
+
+* the O(N) tables the kernels read (`machupx_b200.tables.build_tables`): the mirror's own against the ones flattened from the
+  reference's objects (duck-typed, as oracle/gen_golden.py does), field by field, plus the per-aircraft state block;
+* `MAC`, `get_aircraft_reference_geometry`, `get_max_bound_vortex_length`;
+* every `--solve-every`-th case: the full `solve_forces()` dictionary of the reference against the mirror's, the mirror running
+  on the oracle stand-in devices (tests/oracle_backend.py), to 1e-9;
+* inputs the reference rejects must be rejected by the mirror as well.
+
+Mismatches are printed with the generating input; `--keep` stores the first cases (inputs + the reference's answers) as a
+fixture that tests/test_fuzz_cases.py replays without the reference."""
+import argparse
+import contextlib
+import copy
+import io
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "ref_stubs"))
+
+import machupX as REF  # noqa: E402  the reference
+import machupx_b200 as MIR  # noqa: E402
+import machupx_b200.device as device  # noqa: E402
+import oracle_backend  # noqa: E402
+from machupx_b200 import layout as L  # noqa: E402
+from machupx_b200.tables import build_aircraft_state, build_tables  # noqa: E402
+
+device.DeviceScene = oracle_backend.OracleDeviceScene
+device.BatchDeviceScene = oracle_backend.OracleBatchDeviceScene
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generator
+# ------------------------------------------------------------------------------------------------------------------
+def _dist(rng, lo, hi, allow_step=True):
+    """float, or a span-wise table, sometimes with a step change"""
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        return float(np.round(rng.uniform(lo, hi), 3))
+    n = int(rng.integers(2, 5))
+    s = np.concatenate(([0.0], np.sort(np.round(rng.uniform(0.05, 0.95, n - 2), 3)), [1.0]))
+    v = np.round(rng.uniform(lo, hi, n), 3)
+    rows = [[float(a), float(b)] for a, b in zip(s, v)]
+    if allow_step and kind == 3 and n >= 3:
+        k = 1
+        rows.insert(k + 1, [rows[k][0], float(np.round(rng.uniform(lo, hi), 3))])
+    return rows
+
+
+def _airfoils(rng):
+    out = {}
+    for name in ("af_a", "af_b", "af_c"):
+        out[name] = {"type": "linear", "aL0": float(np.round(rng.uniform(-0.05, 0.01), 4)), "CLa": float(np.round(rng.uniform(5.5, 6.9), 3)),
+                     "CmL0": float(np.round(rng.uniform(-0.08, 0.02), 4)), "Cma": float(np.round(rng.uniform(-0.05, 0.05), 4)),
+                     "CD0": float(np.round(rng.uniform(0.004, 0.01), 5)), "CD1": float(np.round(rng.uniform(-0.002, 0.002), 5)),
+                     "CD2": float(np.round(rng.uniform(0.003, 0.012), 5)), "CL_max": float(np.round(rng.uniform(1.2, 1.6), 2))}
+    return out
+
+
+def _wing(rng, wid, existing, controls, si):
+    w = {"ID": wid, "side": str(rng.choice(["both", "both", "left", "right"])), "is_main": bool(wid == 1)}
+    if existing and rng.random() < 0.6:
+        w["connect_to"] = {"ID": int(rng.choice(existing)), "location": str(rng.choice(["root", "tip"]))}
+    else:
+        w["connect_to"] = {"ID": 0}
+    for key, lo, hi in (("dx", -4.0, 1.0), ("dy", -0.3, 0.3), ("dz", -1.0, 1.0), ("y_offset", 0.0, 0.5)):
+        if rng.random() < 0.4:
+            w["connect_to"][key] = float(np.round(rng.uniform(lo, hi), 3))
+    if rng.random() < 0.12:
+        pts = np.cumsum(np.abs(np.round(rng.uniform(0.3, 1.5, (int(rng.integers(1, 4)), 3)), 3)) * [-0.3, 1.0, -0.1], axis=0)
+        w["quarter_chord_locs"] = pts.tolist()
+    else:
+        w["semispan"] = float(np.round(rng.uniform(1.0, 6.0), 3)) if not si else [float(np.round(rng.uniform(1.0, 6.0), 3)), "ft"]
+        if rng.random() < 0.7:
+            w["sweep"] = _dist(rng, -25.0, 35.0)
+        if rng.random() < 0.6:
+            w["dihedral"] = _dist(rng, -10.0, 80.0 if rng.random() < 0.15 else 12.0)
+    if rng.random() < 0.6:
+        w["twist"] = _dist(rng, -4.0, 5.0)
+    c = rng.random()
+    if c < 0.15:
+        w["chord"] = ["elliptic", float(np.round(rng.uniform(0.5, 1.5), 3))] + (["ft"] if rng.random() < 0.3 else [])
+    elif c < 0.8:
+        w["chord"] = _dist(rng, 0.4, 1.6, allow_step=False)
+    const_sweep = not isinstance(w.get("sweep", 0.0), list) and "quarter_chord_locs" not in w
+    o = rng.random()
+    if o < 0.15 and const_sweep:
+        w["ll_offset"] = "kuchemann"
+    elif o < 0.4:
+        # a span-wise table of offsets is documented (creating_input_files.md:347) but the reference itself trips over it
+        # (wing_segment.py:720 compares the array with "kuchemann"), so only the scalar form can be compared
+        w["ll_offset"] = float(np.round(rng.uniform(-0.05, 0.15), 3))
+    a = rng.random()
+    if a < 0.5:
+        w["airfoil"] = str(rng.choice(["af_a", "af_b", "af_c"]))
+    elif a < 0.85:
+        names = [str(x) for x in rng.choice(["af_a", "af_b", "af_c"], int(rng.integers(2, 4)))]
+        s = np.concatenate(([0.0], np.sort(np.round(rng.uniform(0.1, 0.9, len(names) - 2), 2)), [1.0]))
+        w["airfoil"] = [[float(x), n] for x, n in zip(s, names)]
+    N = int(rng.integers(3, 11))
+    grid = {"N": N}
+    d = rng.random()
+    if d < 0.2:
+        grid["distribution"] = "linear"
+    elif d < 0.3:
+        grid["distribution"] = np.round(np.linspace(0.0, 1.0, 2 * N + 1) ** float(rng.uniform(0.8, 1.3)), 6).tolist()
+    else:
+        if rng.random() < 0.3:
+            grid["flap_edge_cluster"] = bool(rng.random() < 0.5)
+        if rng.random() < 0.2:
+            grid["cluster_points"] = sorted(np.round(rng.uniform(0.2, 0.8, int(rng.integers(1, 3))), 2).tolist())
+    if rng.random() < 0.25:
+        grid["reid_corrections"] = bool(rng.random() < 0.5)
+    if rng.random() < 0.3:
+        grid["joint_length"] = float(np.round(rng.uniform(0.1, 0.3), 3))
+    if rng.random() < 0.3:
+        grid["blending_distance"] = float(np.round(rng.uniform(0.7, 1.5), 3))
+    if rng.random() < 0.2:
+        grid["wing_ID"] = int(rng.integers(1, 3))
+    w["grid"] = grid
+    if controls and rng.random() < 0.6:
+        r0 = float(np.round(rng.uniform(0.0, 0.5), 2))
+        r1 = float(np.round(rng.uniform(r0 + 0.2, 1.0), 2))
+        cs = {"root_span": r0, "tip_span": r1, "control_mixing": {str(k): float(np.round(rng.uniform(-1.0, 1.0), 2))
+                                                                  for k in rng.choice(controls, int(rng.integers(1, len(controls) + 1)), replace=False)}}
+        f = rng.random()
+        if f < 0.4:
+            cs["chord_fraction"] = float(np.round(rng.uniform(0.1, 0.4), 3))
+        elif f < 0.6:
+            cs["chord_fraction"] = [[r0, float(np.round(rng.uniform(0.1, 0.4), 3))], [r1, float(np.round(rng.uniform(0.1, 0.4), 3))]]
+        if rng.random() < 0.3:
+            cs["saturation_angle"] = float(np.round(rng.uniform(5.0, 25.0), 1))
+        if rng.random() < 0.3:
+            cs["is_sealed"] = bool(rng.random() < 0.5)
+        w["control_surface"] = cs
+    return w
+
+
+def _airplane(rng, si):
+    controls = ["aileron", "elevator", "rudder"][:int(rng.integers(0, 4))]
+    ap = {"CG": np.round(rng.uniform(-0.5, 0.5, 3), 3).tolist(), "weight": float(np.round(rng.uniform(10.0, 100.0), 1)),
+          "airfoils": _airfoils(rng), "wings": {}}
+    if controls:
+        ap["controls"] = {c: {"is_symmetric": bool(rng.random() < 0.5)} for c in controls}
+    if rng.random() < 0.4:
+        ap["reference"] = {}
+        if rng.random() < 0.7:
+            ap["reference"]["area"] = float(np.round(rng.uniform(4.0, 12.0), 2))
+        if rng.random() < 0.7:
+            ap["reference"]["longitudinal_length"] = float(np.round(rng.uniform(0.5, 1.5), 2))
+        if rng.random() < 0.7:
+            ap["reference"]["lateral_length"] = float(np.round(rng.uniform(4.0, 10.0), 2))
+    ids = []
+    for k in range(int(rng.integers(1, 5))):
+        wid = k + 1
+        ap["wings"]["seg_%d" % wid] = _wing(rng, wid, ids, controls, si)
+        ids.append(wid)
+    return ap, controls
+
+
+def _state(rng, controls):
+    st = {}
+    if rng.random() < 0.5:
+        st["position"] = np.round(rng.uniform(-50, 50, 3) + [0, 0, -500], 2).tolist()
+    v = rng.random()
+    if v < 0.6:
+        st["velocity"] = float(np.round(rng.uniform(30.0, 200.0), 2))
+        if rng.random() < 0.8:
+            st["alpha"] = float(np.round(rng.uniform(-4.0, 8.0), 3))
+        if rng.random() < 0.6:
+            st["beta"] = float(np.round(rng.uniform(-6.0, 6.0), 3))
+    else:
+        st["velocity"] = np.round([rng.uniform(50, 150), rng.uniform(-8, 8), rng.uniform(-5, 10)], 3).tolist()
+    o = rng.random()
+    if o < 0.3:
+        st["orientation"] = np.round(rng.uniform(-15, 15, 3), 2).tolist()
+    elif o < 0.45:
+        q = rng.normal(size=4) * [1.0, 0.1, 0.1, 0.1] + [2.0, 0, 0, 0]
+        st["orientation"] = (q / np.linalg.norm(q)).tolist()
+    if rng.random() < 0.4:
+        st["angular_rates"] = np.round(rng.uniform(-0.2, 0.2, 3), 3).tolist()
+        if rng.random() < 0.5:
+            st["angular_rate_frame"] = str(rng.choice(["body", "stab", "wind"]))
+    cs = {c: float(np.round(rng.uniform(-8.0, 8.0), 2)) for c in controls if rng.random() < 0.6}
+    return st, cs
+
+
+def make_case(seed):
+    rng = np.random.default_rng(seed)
+    si = rng.random() < 0.25
+    scene = {"tag": "fuzz %d" % seed, "run": {}, "units": "SI" if si else "English",
+             "solver": {"type": "nonlinear" if rng.random() < 0.8 else "linear", "convergence": 1e-10, "relaxation": 1.0, "max_iterations": 100},
+             "scene": {"atmosphere": {}, "aircraft": {}}}
+    for flag in ("use_swept_sections", "use_in_plane", "match_machup_pro"):
+        if rng.random() < 0.12:
+            scene["solver"][flag] = bool(flag == "match_machup_pro")
+    if rng.random() < 0.15:
+        scene["solver"]["constrain_vortex_sheet"] = True
+    if rng.random() < 0.3:
+        scene["scene"]["atmosphere"]["rho"] = "standard" if rng.random() < 0.5 else float(np.round(rng.uniform(0.0015, 0.0024) * (515.4 if si else 1.0), 5))
+    if rng.random() < 0.2:
+        scene["scene"]["atmosphere"]["V_wind"] = np.round(rng.uniform(-10, 10, 3), 2).tolist()
+    for k in range(1 if rng.random() < 0.8 else 2):
+        ap, controls = _airplane(rng, si)
+        st, cs = _state(rng, controls)
+        if k == 1:
+            st["position"] = [float(rng.uniform(-30, -10)), float(rng.uniform(-20, 20)), float(rng.uniform(-5, 5))]
+        scene["scene"]["aircraft"]["plane_%d" % k] = {"file": ap, "state": st, "control_state": cs}
+    return scene
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# comparison
+# ------------------------------------------------------------------------------------------------------------------
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+def _flatten(d, prefix=""):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, dict):
+            out.update(_flatten(v, prefix + str(k) + "/"))
+        else:
+            out[prefix + str(k)] = v
+    return out
+
+
+def compare(case, solve):
+    """Returns (list of mismatch strings, record of the reference's answers)."""
+    issues = []
+    try:
+        ref = _quiet(REF.Scene, copy.deepcopy(case))
+        ref_error = None
+    except Exception as e:                      # noqa: BLE001
+        ref, ref_error = None, e
+    try:
+        mir = _quiet(MIR.Scene, copy.deepcopy(case))
+        mir_error = None
+    except Exception as e:                      # noqa: BLE001
+        mir, mir_error = None, e
+    if ref_error is not None or mir_error is not None:
+        crashed = isinstance(ref_error, (IndexError, KeyError, TypeError, AttributeError)) and mir_error is None
+        if (ref_error is None) != (mir_error is None) and not crashed:
+            issues.append("construction: reference %r, mirror %r" % (ref_error, mir_error))
+        # an IndexError / KeyError / ... out of the reference's own code is the reference tripping over an input it does not
+        # validate (e.g. wing_ID groups that are not contiguous, airplane.py:577), not a rejection the mirror has to copy
+        return issues, {"rejected": type(ref_error).__name__ if ref_error is not None else type(mir_error).__name__,
+                        "reference_crashed": bool(crashed)}
+    record = {"rejected": None}
+    rt, mt = build_tables(ref), mir._tables
+    n = rt["n"]
+    for key in ("n", "ld", "n_aircraft", "n_segments", "flags"):
+        if rt[key] != mt[key]:
+            issues.append("tables[%s]: %r vs %r" % (key, rt[key], mt[key]))
+    if [list(x) for x in rt["segment_names"]] != [list(x) for x in mt["segment_names"]]:
+        issues.append("segment names/order: %r vs %r" % (rt["segment_names"], mt["segment_names"]))
+    if not issues:
+        if not np.array_equal(rt["itab"][:, :n], mt["itab"][:, :n]):
+            rows = np.nonzero((rt["itab"][:, :n] != mt["itab"][:, :n]).any(axis=1))[0]
+            issues.append("itab rows %s differ" % rows.tolist())
+        a, b = rt["tab"][:, :n], mt["tab"][:, :n]
+        if not np.array_equal(np.isfinite(a), np.isfinite(b)):
+            issues.append("tab: non-finite entries in different places (fields %s)" % np.nonzero((np.isfinite(a) != np.isfinite(b)).any(axis=1))[0].tolist())
+        fin = np.isfinite(a) & np.isfinite(b)
+        scale = np.maximum(np.where(fin, np.abs(a), 0.0).max(axis=1, keepdims=True), 1.0)
+        err = np.where(fin, np.abs(np.where(fin, a, 0.0) - np.where(fin, b, 0.0)), 0.0) / scale
+        if not (err.max() < 2e-12):
+            f, i = np.unravel_index(np.nanargmax(err), err.shape)
+            issues.append("tab field %d (cp %d): %.3e" % (f, i, err.max()))
+        if rt["airfoils"].shape != mt["airfoils"].shape or not np.allclose(rt["airfoils"], mt["airfoils"], rtol=0, atol=0):
+            issues.append("airfoil blocks differ")
+        ra, ma = build_aircraft_state(ref), build_aircraft_state(mir)
+        if not np.allclose(ra[:, :L.AC_ZF], ma[:, :L.AC_ZF], rtol=1e-13, atol=1e-12):
+            issues.append("aircraft state block differs by %.3e" % np.abs(ra[:, :L.AC_ZF] - ma[:, :L.AC_ZF]).max())
+    geo = {}
+    for name in case["scene"]["aircraft"]:
+        try:
+            r1, m1 = _quiet(ref.MAC, aircraft=name), _quiet(mir.MAC, aircraft=name)
+            r2, m2 = ref.get_aircraft_reference_geometry(aircraft=name), mir.get_aircraft_reference_geometry(aircraft=name)
+            fr, fm = _flatten(r1), _flatten(m1)
+            for k in fr:
+                if abs(fr[k] - fm.get(k, np.nan)) > 1e-10 * max(1.0, abs(fr[k])):
+                    issues.append("MAC %s: %r vs %r" % (k, fr[k], fm.get(k)))
+            if not np.allclose(r2, m2, rtol=1e-12, atol=1e-12):
+                issues.append("reference geometry: %r vs %r" % (r2, m2))
+            geo[name] = {"MAC": r1, "reference_geometry": [float(x) for x in r2]}
+        except Exception as e:                  # noqa: BLE001
+            issues.append("MAC / reference geometry raised: %r" % (e,))
+    record["geometry"] = geo
+    lr, lm = ref.get_max_bound_vortex_length(), mir.get_max_bound_vortex_length()
+    if abs(lr - lm) > 1e-12 * max(1.0, abs(lr)):
+        issues.append("max bound vortex length: %r vs %r" % (lr, lm))
+    if solve and not issues:
+        kw = {"report_by_segment": True, "stab_frame": True}
+        try:
+            rf = _quiet(ref.solve_forces, **kw)
+            r_err = None
+        except Exception as e:                  # noqa: BLE001
+            rf, r_err = None, e
+        try:
+            mf = _quiet(mir.solve_forces, **kw)
+            m_err = None
+        except Exception as e:                  # noqa: BLE001
+            mf, m_err = None, e
+        if r_err is not None or m_err is not None:
+            if type(r_err).__name__ != type(m_err).__name__:
+                issues.append("solve_forces: reference %r, mirror %r" % (r_err, m_err))
+            record["solve_error"] = type(r_err).__name__ if r_err is not None else None
+        else:
+            fr, fm = _flatten(rf), _flatten(mf)
+            if set(fr) != set(fm):
+                issues.append("FM keys differ: %s" % sorted(set(fr) ^ set(fm))[:6])
+            nan_r = sorted(k for k in fr if not np.isfinite(fr[k]))
+            nan_m = sorted(k for k in fm if not np.isfinite(fm[k]))
+            if nan_r != nan_m:
+                issues.append("FM: non-finite entries differ (%d in the reference, %d in the mirror)" % (len(nan_r), len(nan_m)))
+            scale = max([1.0] + [abs(v) for v in fr.values() if np.isfinite(v)])
+            worst = max(((abs(fr[k] - fm[k]), k) for k in fr if k in fm and np.isfinite(fr[k]) and np.isfinite(fm[k])), default=(0.0, ""))
+            record["non_finite"] = len(nan_r)
+            if not (worst[0] <= 1e-9 * scale):
+                issues.append("FM %s differs by %.3e (scale %.3e)" % (worst[1], worst[0], scale))
+            record["FM"] = rf
+    return issues, record
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=200)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--solve-every", type=int, default=4)
+    ap.add_argument("--keep", default=None)
+    ap.add_argument("--keep-count", type=int, default=24)
+    args = ap.parse_args()
+    bad, rejected, solved, kept, crashed = 0, 0, 0, [], 0
+    for k in range(args.cases):
+        seed = args.seed + k
+        case = make_case(seed)
+        solve = args.solve_every > 0 and k % args.solve_every == 0
+        issues, record = compare(case, solve)
+        rejected += record.get("rejected") is not None and not record.get("reference_crashed")
+        crashed += bool(record.get("reference_crashed"))
+        solved += "FM" in record
+        if issues:
+            bad += 1
+            print("seed %d: %s" % (seed, "; ".join(issues)))
+        elif args.keep and len(kept) < args.keep_count and record.get("rejected") is None and "FM" in record:
+            kept.append({"seed": seed, "input": case, "reference": record})
+    print("%d cases, %d with mismatches, %d rejected by both, %d where only the reference crashed (unvalidated input), %d solved and compared"
+          % (args.cases, bad, rejected, crashed, solved))
+    if args.keep:
+        with open(args.keep, "w") as fh:
+            json.dump({"generator": "oracle/fuzz_host_mirror.py --seed %d" % args.seed, "cases": kept}, fh)
+        print("kept %d cases in %s" % (len(kept), args.keep))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,62 @@
+"""Replay of differential-fuzzer cases (oracle/fuzz_host_mirror.py --keep tests/golden/fuzz_cases.json): random scenes -- every
+documented way of giving span-wise distributions, segment connections, grids, control surfaces and units, one or two aircraft,
+random flight / control states and solver flags -- whose `solve_forces()` dictionaries, mean aerodynamic chords and reference
+geometries were computed by the UNMODIFIED reference when the fixture was generated.  Here the same inputs go through
+machupx_b200 with the oracle stand-in devices, so the test runs without the reference and without a GPU; what it protects is the
+host mirror (geometry, tables, frames, result dictionaries) together with the oracle across the input space, not one aeroplane."""
+import copy
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import oracle_backend
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "fuzz_cases.json")) as fh:
+    FIXTURE = json.load(fh)
+CASES = FIXTURE["cases"]
+
+
+def _flatten(d, prefix=""):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, dict):
+            out.update(_flatten(v, prefix + str(k) + "/"))
+        else:
+            out[prefix + str(k)] = v
+    return out
+
+
+def test_fixture_covers_the_input_space():
+    text = json.dumps([c["input"] for c in CASES])
+    for feature in ("quarter_chord_locs", "elliptic", "kuchemann", "cluster_points", "reid_corrections", "joint_length", "blending_distance",
+                    "wing_ID", "saturation_angle", "is_sealed", "angular_rate_frame", "constrain_vortex_sheet", "V_wind", '"SI"',
+                    '"location": "root"', '"side": "left"', '"side": "right"', "y_offset"):
+        assert feature in text, feature
+    assert sum(len(c["input"]["scene"]["aircraft"]) == 2 for c in CASES) >= 2
+
+
+@pytest.mark.parametrize("k", range(len(CASES)), ids=["seed%d" % c["seed"] for c in CASES])
+def test_fuzz_case_against_the_reference(monkeypatch, k):
+    oracle_backend.install(monkeypatch)
+    from machupx_b200 import Scene
+    case, ref = CASES[k]["input"], CASES[k]["reference"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scene = Scene(copy.deepcopy(case))
+        for name, geo in ref["geometry"].items():
+            mac = _flatten(scene.MAC(aircraft=name))
+            for key, value in _flatten(geo["MAC"]).items():
+                assert abs(mac[key] - value) <= 1e-10 * max(1.0, abs(value)), (name, key)
+            assert np.allclose(scene.get_aircraft_reference_geometry(aircraft=name), geo["reference_geometry"], rtol=1e-12, atol=1e-12)
+        got = _flatten(scene.solve_forces(report_by_segment=True, stab_frame=True))
+    want = _flatten(ref["FM"])
+    assert set(got) == set(want)
+    finite = [key for key in want if want[key] is not None and np.isfinite(want[key])]
+    assert sorted(key for key in got if np.isfinite(got[key])) == sorted(finite)          # NaN where the reference has NaN
+    scale = max([1.0] + [abs(want[key]) for key in finite])
+    worst = max(abs(got[key] - want[key]) for key in finite) if finite else 0.0
+    assert worst <= 1e-9 * scale, worst
