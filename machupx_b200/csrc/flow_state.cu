@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(128) flow_state_kernel(int n, int ld, int flag
     W[(size_t)W_CLA0 * ld + i] = CLa;
     W[(size_t)W_CL0 * ld + i] = CL;
     out[(size_t)LLS_O_AL0 * ld + i] = aL0;
+    // what the reference's _CL holds after a LINEAR solve (scene.py:659-666; distributions() reports it as section_CL); every
+    // residual evaluation of a nonlinear solve overwrites it (scene.py:765-779)
+    out[(size_t)LLS_O_CL * ld + i] = CL;
 }
 
 int launch_flow_state(Scene* s, cudaStream_t st) {

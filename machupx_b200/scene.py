@@ -695,6 +695,8 @@ class Scene:
                 ap.set_control_state(saved_controls)
 
         rows, tabs, frames = [], [], []
+        if not setters:          # e.g. the control stencil of an aircraft without controls: nothing to solve
+            return []
         try:
             for perturb in setters:
                 restore()
@@ -870,10 +872,18 @@ class Scene:
             orig = {"position": np.asarray(p0, dtype=float), "velocity": earth_to_body(q0, v0 - self._get_wind(p0)),
                     "orientation": q0, "angular_rates": np.asarray(w0, dtype=float)}
             d = {}
+            # The reference refreshes the scene geometry only for the position and orientation perturbations (scene.py:2383,
+            # 2390): its angular-rate perturbations, which come right after the backward z_f one, are solved with the geometry and
+            # the atmosphere at the control points of THAT position (1.5e-5 relative in a standard atmosphere).  This package always
+            # solves the state it is given, so it is given that position for those six solves and the numbers come out the same.
+            stale = copy.deepcopy(orig)
+            stale["position"][2] += dx
+            stale["position"][2] -= 2.0 * dx
+            base = {"angular_rates": stale}
             if batched:      # the 24 stencil points (12 of them move or rotate the aircraft: per-case tables) in one device pass
                 setters = []
                 for variable, tag, index, step in plan:
-                    setters += self._state_stencil(variable, index, step, orig)
+                    setters += self._state_stencil(variable, index, step, base.get(variable, orig))
                 tot = self._stencil_totals(name, setters, {k: v for k, v in kwargs.items() if k != "filename"})
                 for i, (variable, tag, index, step) in enumerate(plan):
                     f, b = tot[2 * i], tot[2 * i + 1]
@@ -881,7 +891,7 @@ class Scene:
                 derivs[name] = d
                 continue
             for variable, tag, index, step in plan:
-                d.update(self._determine_state_derivs(variable, tag, index, step, orig, name, **kwargs))
+                d.update(self._determine_state_derivs(variable, tag, index, step, base.get(variable, orig), name, **kwargs))
             derivs[name] = d
             ap.set_state(**orig)
             self._solved = False

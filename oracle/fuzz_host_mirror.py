@@ -12,6 +12,9 @@ connections, grids, control surfaces, units; random flight and control state; ra
 * `MAC`, `get_aircraft_reference_geometry`, `get_max_bound_vortex_length`;
 * every `--solve-every`-th case: the full `solve_forces()` dictionary of the reference against the mirror's, the mirror running
   on the oracle stand-in devices (tests/oracle_backend.py), to 1e-9;
+* every `--drivers-every`-th solvable case: `derivatives()` (stability, damping, control), `state_derivatives()`, `aero_center()`
+  and `distributions()` of the reference against the mirror's, sequential AND `batched=True` (the batched finite-difference
+  stencils with per-case tables), relative 1e-6 (finite differences of two solves converged to 1e-10);
 * inputs the reference rejects must be rejected by the mirror as well.
 
 Mismatches are printed with the generating input; `--keep` stores the first cases (inputs + the reference's answers) as a
@@ -342,15 +345,79 @@ def compare(case, solve):
     return issues, record
 
 
+def _same(a, b, tol, path, issues):
+    if isinstance(a, dict):
+        if not isinstance(b, dict) or set(a) != set(b):
+            issues.append("%s: keys differ" % path)
+            return
+        for k in a:
+            _same(a[k], b[k], tol, path + "/" + str(k), issues)
+        return
+    x, y = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    if x.shape != y.shape:
+        issues.append("%s: shape %s vs %s" % (path, x.shape, y.shape))
+        return
+    fin = np.isfinite(x)
+    if not np.array_equal(fin, np.isfinite(y)):
+        issues.append("%s: non-finite entries differ" % path)
+        return
+    if fin.any():
+        scale = max(1.0, np.abs(x[fin]).max())
+        err = np.abs(x[fin] - y[fin]).max()
+        if not (err <= tol * scale):
+            issues.append("%s: %.3e (scale %.3e)" % (path, err, scale))
+
+
+def compare_drivers(case):
+    """derivatives / state_derivatives / aero_center / distributions of the reference against the mirror (sequential and batched)."""
+    issues, results = [], {}
+    calls = [("derivatives", {}, 1e-6), ("state_derivatives", {}, 1e-6), ("aero_center", {}, 1e-6), ("distributions", {}, 1e-8)]
+    for method, kw, tol in calls:
+        ref = _quiet(REF.Scene, copy.deepcopy(case))          # a fresh scene per driver, on both sides
+        try:
+            want = _quiet(getattr(ref, method), **kw)
+            r_err = None
+        except Exception as e:                  # noqa: BLE001
+            want, r_err = None, e
+        if r_err is None:
+            results[method] = _jsonable(want)
+        for batched in ((False, True) if method != "distributions" else (False,)):
+            mir = _quiet(MIR.Scene, copy.deepcopy(case))
+            try:
+                got = _quiet(getattr(mir, method), **(dict(kw, batched=True) if batched else kw))
+                m_err = None
+            except Exception as e:              # noqa: BLE001
+                got, m_err = None, e
+            label = method + (" (batched)" if batched else "")
+            if r_err is not None or m_err is not None:
+                if type(r_err).__name__ != type(m_err).__name__:
+                    issues.append("%s: reference %r, mirror %r" % (label, r_err, m_err))
+                continue
+            _same(want, got, tol, label, issues)
+    return issues, results
+
+
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {str(k): _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple, np.ndarray)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, (np.floating, np.integer)):
+        return x.item()
+    return x
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--solve-every", type=int, default=4)
+    ap.add_argument("--drivers-every", type=int, default=0)
     ap.add_argument("--keep", default=None)
     ap.add_argument("--keep-count", type=int, default=24)
+    ap.add_argument("--keep-drivers", type=int, default=6)
     args = ap.parse_args()
-    bad, rejected, solved, kept, crashed = 0, 0, 0, [], 0
+    bad, rejected, solved, kept, crashed, drivers = 0, 0, 0, [], 0, 0
     for k in range(args.cases):
         seed = args.seed + k
         case = make_case(seed)
@@ -359,13 +426,18 @@ def main():
         rejected += record.get("rejected") is not None and not record.get("reference_crashed")
         crashed += bool(record.get("reference_crashed"))
         solved += "FM" in record
+        if not issues and args.drivers_every > 0 and k % args.drivers_every == 0 and record.get("rejected") is None \
+                and len(case["scene"]["aircraft"]) == 1 and not record.get("non_finite") and "FM" in record:
+            issues, record["drivers"] = compare_drivers(case)
+            drivers += 1
         if issues:
             bad += 1
             print("seed %d: %s" % (seed, "; ".join(issues)))
-        elif args.keep and len(kept) < args.keep_count and record.get("rejected") is None and "FM" in record:
+        elif args.keep and record.get("rejected") is None and "FM" in record and (
+                len(kept) < args.keep_count or ("drivers" in record and sum("drivers" in c["reference"] for c in kept) < args.keep_drivers)):
             kept.append({"seed": seed, "input": case, "reference": record})
-    print("%d cases, %d with mismatches, %d rejected by both, %d where only the reference crashed (unvalidated input), %d solved and compared"
-          % (args.cases, bad, rejected, crashed, solved))
+    print("%d cases, %d with mismatches, %d rejected by both, %d where only the reference crashed (unvalidated input), %d solved and compared, "
+          "%d with their drivers compared" % (args.cases, bad, rejected, crashed, solved, drivers))
     if args.keep:
         with open(args.keep, "w") as fh:
             json.dump({"generator": "oracle/fuzz_host_mirror.py --seed %d" % args.seed, "cases": kept}, fh)

@@ -62,9 +62,26 @@ class OracleDeviceScene:
         return 0
 
     def out(self):
+        """The per-control-point result table the kernels leave behind (enum lls_out_field), from the oracle's intermediate
+        results: what flow_state_kernel, the last residual and integrate_kernel write."""
+        res, D, F = self._res, self._res["dist"], self._res["flow"]
         out = np.zeros((L.NO, self.n))
-        out[L.O_GAMMA] = self._res["gamma"]
-        out[L.O_VI:L.O_VI + 3] = np.asarray(self._res["dist"]["v_i"]).T
+        out[L.O_GAMMA] = res["gamma"]
+        out[L.O_VI:L.O_VI + 3] = np.asarray(D["v_i"]).T
+        out[L.O_ALPHA], out[L.O_CD], out[L.O_CM], out[L.O_RE], out[L.O_MACH] = D["alpha"], D["CD"], D["Cm"], D["Re"], D["M"]
+        for f, key in ((L.O_DFINV, "dF_inv"), (L.O_DMINV, "dM_inv"), (L.O_DFVISC, "dF_visc"), (L.O_DMVISC, "dM_visc")):
+            out[f:f + 3] = np.asarray(D[key]).T
+        out[L.O_AL0] = F.aL0
+        out[L.O_REDIM_FULL] = D["redim_full"]
+        if D["redim_in_plane"] is not None:
+            out[L.O_REDIM_IP] = D["redim_in_plane"]
+        out[L.O_UTRAIL0:L.O_UTRAIL0 + 3], out[L.O_UTRAIL1:L.O_UTRAIL1 + 3] = F.u_trailing_0.T, F.u_trailing_1.T
+        out[L.O_VI2] = D["V_i_2"]
+        if self._solver[0] == "nonlinear":       # section lift of the last residual evaluation (scene.py:911-913)
+            T = O.Tables(self.tables, self.ac)
+            out[L.O_CL] = O.residual(T, F, res["V"], res["gamma"]).CL
+        else:                                    # a linear solve leaves the flow-state estimate (scene.py:659-666)
+            out[L.O_CL] = F.CL
         return out
 
 

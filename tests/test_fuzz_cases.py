@@ -3,7 +3,14 @@ documented way of giving span-wise distributions, segment connections, grids, co
 random flight / control states and solver flags -- whose `solve_forces()` dictionaries, mean aerodynamic chords and reference
 geometries were computed by the UNMODIFIED reference when the fixture was generated.  Here the same inputs go through
 machupx_b200 with the oracle stand-in devices, so the test runs without the reference and without a GPU; what it protects is the
-host mirror (geometry, tables, frames, result dictionaries) together with the oracle across the input space, not one aeroplane."""
+host mirror (geometry, tables, frames, result dictionaries) together with the oracle across the input space, not one aeroplane.
+Six of the cases also carry the reference's `derivatives()`, `state_derivatives()`, `aero_center()` and `distributions()`; they are
+replayed sequentially and with `batched=True` (the batched finite-difference stencils with per-case tables).
+
+What the fuzzer has found so far (all fixed or reproduced): a batched control stencil of an aircraft without controls crashed; a
+zero lateral reference length raised where the reference returns inf; the reference solves the angular-rate perturbations of
+`state_derivatives()` with the atmosphere of the previous position perturbation (scene.py:2383-2390; reproduced, 1.5e-5 in a
+standard atmosphere); `section_CL` after a LINEAR solve is the flow-state estimate (scene.py:659-666)."""
 import copy
 import json
 import os
@@ -60,3 +67,37 @@ def test_fuzz_case_against_the_reference(monkeypatch, k):
     scale = max([1.0] + [abs(want[key]) for key in finite])
     worst = max(abs(got[key] - want[key]) for key in finite) if finite else 0.0
     assert worst <= 1e-9 * scale, worst
+
+
+DRIVER_CASES = [k for k, c in enumerate(CASES) if "drivers" in c["reference"]]
+
+
+def _same(want, got, tol, path=""):
+    if isinstance(want, dict):
+        assert isinstance(got, dict) and set(want) == set(got), path
+        for key in want:
+            _same(want[key], got[key], tol, path + "/" + str(key))
+        return
+    x, y = np.asarray(want, dtype=float), np.asarray(got, dtype=float)
+    assert x.shape == y.shape, path
+    fin = np.isfinite(x)
+    assert np.array_equal(fin, np.isfinite(y)), path
+    if fin.any():
+        assert np.abs(x[fin] - y[fin]).max() <= tol * max(1.0, np.abs(x[fin]).max()), path
+
+
+@pytest.mark.parametrize("batched", [False, True], ids=["sequential", "batched"])
+@pytest.mark.parametrize("k", DRIVER_CASES, ids=["seed%d" % CASES[k]["seed"] for k in DRIVER_CASES])
+def test_fuzz_case_drivers_against_the_reference(monkeypatch, k, batched):
+    oracle_backend.install(monkeypatch)
+    from machupx_b200 import Scene
+    case, ref = CASES[k]["input"], CASES[k]["reference"]["drivers"]
+    assert set(ref) == {"derivatives", "state_derivatives", "aero_center", "distributions"}
+    for method, tol in (("derivatives", 1e-6), ("state_derivatives", 1e-6), ("aero_center", 1e-6), ("distributions", 1e-8)):
+        if method == "distributions" and batched:
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            scene = Scene(copy.deepcopy(case))                        # a fresh scene per driver, as when the fixture was made
+            got = getattr(scene, method)(**({"batched": True} if batched else {}))
+        _same(ref[method], got, tol, method)
