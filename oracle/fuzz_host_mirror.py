@@ -413,10 +413,14 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--solve-every", type=int, default=4)
     ap.add_argument("--drivers-every", type=int, default=0)
+    ap.add_argument("--sessions", type=int, default=0, help="session mode: that many random call sequences instead of single cases")
+    ap.add_argument("--session-length", type=int, default=12)
     ap.add_argument("--keep", default=None)
     ap.add_argument("--keep-count", type=int, default=24)
     ap.add_argument("--keep-drivers", type=int, default=6)
     args = ap.parse_args()
+    if args.sessions:
+        return main_sessions(args)
     bad, rejected, solved, kept, crashed, drivers = 0, 0, 0, [], 0, 0
     for k in range(args.cases):
         seed = args.seed + k
@@ -442,6 +446,102 @@ def main():
         with open(args.keep, "w") as fh:
             json.dump({"generator": "oracle/fuzz_host_mirror.py --seed %d" % args.seed, "cases": kept}, fh)
         print("kept %d cases in %s" % (len(kept), args.keep))
+    return 1 if bad else 0
+
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# session mode: a random SEQUENCE of API calls on one scene, applied to the reference and to the mirror, compared call by call
+# (what it exercises is the mirror's caching: table revisions, row uploads, state uploads, batch devices)
+# ------------------------------------------------------------------------------------------------------------------
+def _session_ops(rng, case, length):
+    """Odd sessions run the drivers batched and never ask for initial_guess="previous" (a batched stencil does not leave its last
+    perturbed circulation behind as the reference's sequential drivers do, so "previous" would start elsewhere -- harmless unless
+    the scene has several solutions, e.g. beyond CL_max); even sessions are purely sequential and use "previous" freely."""
+    names = list(case["scene"]["aircraft"])
+    ops = []
+    use_batched = bool(rng.integers(0, 2))
+    for _ in range(length):
+        name = str(rng.choice(names))
+        controls = list(case["scene"]["aircraft"][name]["file"].get("controls", {}))
+        kind = rng.choice(["state", "state", "controls", "solve", "solve", "solve", "stability", "control_derivs", "aero_center",
+                           "target_CL", "pitch_trim", "distributions", "max_length"])
+        if kind == "state":
+            st, _ = _state(rng, controls)
+            ops.append(("set_aircraft_state", {"state": st, "aircraft": name}))
+        elif kind == "controls":
+            cs = {c: float(np.round(rng.uniform(-8.0, 8.0), 2)) for c in controls if rng.random() < 0.7}
+            ops.append(("set_aircraft_control_state", {"control_state": cs, "aircraft": name}))
+        elif kind == "solve":
+            kw = {"report_by_segment": bool(rng.random() < 0.5), "non_dimensional": bool(rng.random() < 0.7), "dimensional": bool(rng.random() < 0.7),
+                  "body_frame": bool(rng.random() < 0.7), "stab_frame": bool(rng.random() < 0.5), "wind_frame": bool(rng.random() < 0.7)}
+            if rng.random() < 0.3 and not use_batched:
+                kw["initial_guess"] = "previous"
+            ops.append(("solve_forces", kw))
+        elif kind == "stability":
+            ops.append(("stability_derivatives", {"aircraft": name, "batched": use_batched and bool(rng.random() < 0.7)}))
+        elif kind == "control_derivs":
+            ops.append(("control_derivatives", {"aircraft": name, "batched": use_batched and bool(rng.random() < 0.7)}))
+        elif kind == "aero_center":
+            ops.append(("aero_center", {"aircraft": name, "batched": use_batched and bool(rng.random() < 0.7)}))
+        elif kind == "target_CL":
+            ops.append(("target_CL", {"aircraft": name, "CL": float(np.round(rng.uniform(0.1, 0.6), 2)), "set_state": bool(rng.random() < 0.5),
+                                      "batched": use_batched and bool(rng.random() < 0.7)}))
+        elif kind == "pitch_trim":
+            ops.append(("pitch_trim", {"aircraft": name, "set_trim_state": bool(rng.random() < 0.5), "batched": use_batched and bool(rng.random() < 0.7)}))
+        elif kind == "distributions":
+            ops.append(("distributions", {}))
+        else:
+            ops.append(("get_max_bound_vortex_length", {}))
+    return ops
+
+
+def run_session(seed, length):
+    rng = np.random.default_rng(10 ** 6 + seed)
+    case = make_case(seed)
+    try:
+        ref = _quiet(REF.Scene, copy.deepcopy(case))
+        mir = _quiet(MIR.Scene, copy.deepcopy(case))
+    except Exception:                            # noqa: BLE001  (construction is what the case mode compares)
+        return [], 0
+    issues = []
+    ops = _session_ops(rng, case, length)
+    for step, (method, kw) in enumerate(ops):
+        kr = {k: v for k, v in kw.items() if k != "batched"}
+        try:
+            want, r_err = _quiet(getattr(ref, method), **copy.deepcopy(kr)), None
+        except Exception as e:                  # noqa: BLE001
+            want, r_err = None, e
+        try:
+            got, m_err = _quiet(getattr(mir, method), **copy.deepcopy(kw)), None
+        except Exception as e:                  # noqa: BLE001
+            got, m_err = None, e
+        label = "step %d %s(%s)" % (step, method, ", ".join("%s=%r" % kv for kv in kw.items() if kv[0] not in ("state", "control_state")))
+        if r_err is not None or m_err is not None:
+            if isinstance(r_err, (UnboundLocalError, IndexError, KeyError, TypeError, AttributeError)) and m_err is None:
+                break                            # the reference tripped over its own code (e.g. pitch_trim's `alpha1`, scene.py:2560): no verdict
+            if type(r_err).__name__ != type(m_err).__name__:
+                issues.append("%s: reference %r, mirror %r" % (label, r_err, m_err))
+            break        # after an exception (a trim that diverged, ...) the two scenes are no longer known to be in the same state
+        if want is None and got is None:
+            continue
+        before = len(issues)
+        _same(_jsonable(want) if not np.isscalar(want) else float(want), _jsonable(got) if not np.isscalar(got) else float(got),
+              1e-6 if method not in ("solve_forces", "distributions", "get_max_bound_vortex_length") else 1e-9, label, issues)
+        if len(issues) > before:
+            break
+    return issues, len(ops)
+
+
+def main_sessions(args):
+    bad = steps = 0
+    for k in range(args.sessions):
+        issues, n = run_session(args.seed + k, args.session_length)
+        steps += n
+        if issues:
+            bad += 1
+            print("session %d: %s" % (args.seed + k, "; ".join(issues[:4])))
+    print("%d sessions (%d calls), %d with mismatches" % (args.sessions, steps, bad))
     return 1 if bad else 0
 
 

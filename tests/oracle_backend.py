@@ -41,16 +41,31 @@ class OracleDeviceScene:
 
     def flow_state(self):
         self._solver = ("none",)
+        self._linear_start = False
 
     def build_influence(self, impingement_threshold=1e-10):
         pass
 
     def solve_linear(self):
         self._solver = ("linear",)
+        self._linear_start = True
 
     def solve_nonlinear(self, convergence, relaxation, max_iterations):
         self._solver = ("nonlinear", convergence, relaxation, max_iterations)
-        self._res, status = _solve(self.tables, self.ac, "nonlinear", convergence, relaxation, max_iterations)
+        if self._linear_start or getattr(self, "_res", None) is None:
+            self._res, status = _solve(self.tables, self.ac, "nonlinear", convergence, relaxation, max_iterations)
+        else:
+            # initial_guess="previous" (scene.py:1462-1478): Newton starts from the circulation the last solve left in the result
+            # table -- after its integration, i.e. rescaled if match_machup_pro is set (scene.py:938-939)
+            T = O.Tables(self.tables, self.ac)
+            F = O.flow_state(T)
+            V = O.influence(T, F)
+            gamma, it, err, ok, hist = O.solve_nonlinear(T, F, V, np.array(self._res["dist"]["gamma"], copy=True), convergence, relaxation,
+                                                         max_iterations)
+            seg, D = O.integrate(T, F, V, gamma)
+            self._res = {"flow": F, "V": V, "gamma": gamma, "iterations": it, "error": err, "converged": ok, "history": hist,
+                         "seg_fm": seg, "dist": D}
+            status = 0 if ok else L.STATUS_NOT_CONVERGED
         return self._res["iterations"], self._res["error"], status, list(self._res["history"])
 
     def integrate(self):
@@ -66,7 +81,7 @@ class OracleDeviceScene:
         results: what flow_state_kernel, the last residual and integrate_kernel write."""
         res, D, F = self._res, self._res["dist"], self._res["flow"]
         out = np.zeros((L.NO, self.n))
-        out[L.O_GAMMA] = res["gamma"]
+        out[L.O_GAMMA] = D["gamma"]             # with match_machup_pro the integration rescales it in place (scene.py:938-939)
         out[L.O_VI:L.O_VI + 3] = np.asarray(D["v_i"]).T
         out[L.O_ALPHA], out[L.O_CD], out[L.O_CM], out[L.O_RE], out[L.O_MACH] = D["alpha"], D["CD"], D["Cm"], D["Re"], D["M"]
         for f, key in ((L.O_DFINV, "dF_inv"), (L.O_DMINV, "dM_inv"), (L.O_DFVISC, "dF_visc"), (L.O_DMVISC, "dM_visc")):
