@@ -394,7 +394,88 @@ def compare_drivers(case):
                     issues.append("%s: reference %r, mirror %r" % (label, r_err, m_err))
                 continue
             _same(want, got, tol, label, issues)
+    issues += compare_sweep(case)
+    issues += compare_pylot_model(case)
     return issues, results
+
+
+def compare_pylot_model(case):
+    """export_pylot_model (59 solves: reference state, every derivative, two 21-state polars): the JSON file the reference writes
+    against the one the mirror writes, sequential and batched."""
+    import tempfile
+    issues = []
+    with tempfile.TemporaryDirectory() as tmp:
+        files = {}
+        for label, module, kw in (("reference", REF, {}), ("mirror", MIR, {}), ("mirror (batched)", MIR, {"batched": True})):
+            path = os.path.join(tmp, label.replace(" ", "_") + ".json")
+            try:
+                scene = _quiet(module.Scene, copy.deepcopy(case))
+                _quiet(scene.export_pylot_model, filename=path, **kw)
+                with open(path) as fh:
+                    files[label] = json.load(fh)
+            except Exception as e:              # noqa: BLE001
+                files[label] = e
+        want = files["reference"]
+        for label in ("mirror", "mirror (batched)"):
+            got = files[label]
+            if isinstance(want, Exception) or isinstance(got, Exception):
+                if type(want).__name__ != type(got).__name__ and not isinstance(want, (UnboundLocalError, IndexError, KeyError, TypeError)):
+                    issues.append("export_pylot_model %s: reference %r, got %r" % (label, want, got))
+                continue
+            _same_model(want, got, "export_pylot_model %s" % label, issues)
+    return issues
+
+
+def _same_model(want, got, path, issues):
+    if isinstance(want, dict):
+        if not isinstance(got, dict) or set(want) != set(got):
+            issues.append("%s: keys %s" % (path, sorted(set(want) ^ set(got if isinstance(got, dict) else []))[:6]))
+            return
+        for k in want:
+            _same_model(want[k], got[k], path + "/" + str(k), issues)
+    elif isinstance(want, list):
+        if not isinstance(got, list) or len(want) != len(got):
+            issues.append("%s: list length" % path)
+            return
+        for i, (a, b) in enumerate(zip(want, got)):
+            _same_model(a, b, path + "[%d]" % i, issues)
+    elif isinstance(want, (int, float)) and not isinstance(want, bool):
+        if not isinstance(got, (int, float)) or not (abs(want - got) <= 1e-6 * max(1.0, abs(want)) or (want != want and got != got)):
+            issues.append("%s: %r vs %r" % (path, want, got))
+    elif want != got:
+        issues.append("%s: %r vs %r" % (path, want, got))
+
+
+def compare_sweep(case, nstates=6):
+    """An alpha / beta / airspeed sweep: the reference's loop of set_aircraft_state + solve_forces against ONE
+    Scene.solve_forces_batch call of the mirror."""
+    issues = []
+    name = list(case["scene"]["aircraft"])[0]
+    rng = np.random.default_rng(77)
+    pos = case["scene"]["aircraft"][name]["state"].get("position", [0.0, 0.0, 0.0])
+    states = [{"position": list(pos), "velocity": float(np.round(rng.uniform(60.0, 160.0), 2)), "alpha": float(np.round(rng.uniform(-3.0, 7.0), 2)),
+               "beta": float(np.round(rng.uniform(-5.0, 5.0), 2))} for _ in range(nstates)]
+    ref = _quiet(REF.Scene, copy.deepcopy(case))
+    mir = _quiet(MIR.Scene, copy.deepcopy(case))
+    try:
+        mir.set_aircraft_state(state=copy.deepcopy(states[0]), aircraft=name)       # level flight at the sweep's position: the pose the batch keeps
+        got = _quiet(mir.solve_forces_batch, copy.deepcopy(states), aircraft=name)
+    except Exception as e:                      # noqa: BLE001
+        return ["solve_forces_batch raised %r" % (e,)]
+    for i, st in enumerate(states):
+        try:
+            _quiet(ref.set_aircraft_state, state=copy.deepcopy(st), aircraft=name)
+            want = _quiet(ref.solve_forces)[name]["total"]
+        except Exception as e:                  # noqa: BLE001
+            if bool(got["converged"][i]):
+                issues.append("sweep state %d: reference %r, batch converged" % (i, e))
+            continue
+        for key, value in want.items():
+            mine = got["totals"][name][key][i]
+            if np.isfinite(value) != np.isfinite(mine) or (np.isfinite(value) and abs(mine - value) > 1e-9 * max(1.0, abs(value))):
+                issues.append("sweep state %d %s: %r vs %r" % (i, key, value, mine))
+                break
+    return issues
 
 
 def _jsonable(x):
