@@ -76,6 +76,29 @@ def _airfoils(rng):
     return out
 
 
+def _database_tables(rng, directory, seed):
+    """Two synthetic (alpha, Rey) tables on a JITTERED grid: no two cells are co-circular, so the Delaunay triangulation -- and
+    with it airfoil_db's interpolant -- is unique (the reference's own tables are exact grids, see recover_database_pin.py)."""
+    out = {}
+    for name in ("af_a", "af_b", "af_c"):
+        a = np.radians(np.arange(-22.0, 24.1, 2.0))
+        r = np.array([4e4, 1.5e5, 5e5, 1.2e6, 3e6, 8e6, 2.5e7])
+        A, R = np.meshgrid(a, r, indexing="ij")
+        A = A + rng.uniform(-0.006, 0.006, A.shape)
+        R = R * (1.0 + rng.uniform(-0.08, 0.08, R.shape))
+        a0, cla = rng.uniform(-0.05, 0.0), rng.uniform(5.6, 6.6)
+        CL = cla * (1.0 + 0.03 * np.log10(R / 1e6)) * np.tanh((A - a0) / 0.35) * 0.35
+        CD = 0.007 * (R / 1e6) ** -0.15 + 0.011 * CL * CL
+        Cm = rng.uniform(-0.07, 0.0) + 0.01 * CL
+        path = os.path.join(directory, "fuzz_%d_%s.txt" % (seed, name))
+        with open(path, "w") as fh:
+            fh.write("# alpha\tRey\tCL\tCD\tCm\n")
+            for row in zip(A.ravel(), R.ravel(), CL.ravel(), CD.ravel(), Cm.ravel()):
+                fh.write("\t".join("%.10e" % v for v in row) + "\n")
+        out[name] = {"type": "database", "input_file": path}
+    return out
+
+
 def _wing(rng, wid, existing, controls, si):
     w = {"ID": wid, "side": str(rng.choice(["both", "both", "left", "right"])), "is_main": bool(wid == 1)}
     if existing and rng.random() < 0.6:
@@ -204,7 +227,9 @@ def _state(rng, controls):
     return st, cs
 
 
-def make_case(seed):
+def make_case(seed, database_dir=None):
+    """database_dir: where to write synthetic airfoil tables; every case then uses "database" airfoils (their file paths go into
+    the input, so such cases are not kept as fixtures)."""
     rng = np.random.default_rng(seed)
     si = rng.random() < 0.25
     scene = {"tag": "fuzz %d" % seed, "run": {}, "units": "SI" if si else "English",
@@ -224,6 +249,8 @@ def make_case(seed):
         st, cs = _state(rng, controls)
         if k == 1:
             st["position"] = [float(rng.uniform(-30, -10)), float(rng.uniform(-20, 20)), float(rng.uniform(-5, 5))]
+        if database_dir is not None:
+            ap["airfoils"] = _database_tables(rng, database_dir, seed * 10 + k)
         scene["scene"]["aircraft"]["plane_%d" % k] = {"file": ap, "state": st, "control_state": cs}
     return scene
 
@@ -269,7 +296,12 @@ def compare(case, solve):
         return issues, {"rejected": type(ref_error).__name__ if ref_error is not None else type(mir_error).__name__,
                         "reference_crashed": bool(crashed)}
     record = {"rejected": None}
-    rt, mt = build_tables(ref), mir._tables
+    database = '"database"' in json.dumps(case)
+    mt = mir._tables
+    if database:        # the stand-in's database airfoils have no parameter block to flatten; the solves below compare them
+        rt = dict(mt)
+    else:
+        rt = build_tables(ref)
     n = rt["n"]
     for key in ("n", "ld", "n_aircraft", "n_segments", "flags"):
         if rt[key] != mt[key]:
@@ -461,7 +493,14 @@ def compare_sweep(case, nstates=6):
         mir.set_aircraft_state(state=copy.deepcopy(states[0]), aircraft=name)       # level flight at the sweep's position: the pose the batch keeps
         got = _quiet(mir.solve_forces_batch, copy.deepcopy(states), aircraft=name)
     except Exception as e:                      # noqa: BLE001
-        return ["solve_forces_batch raised %r" % (e,)]
+        # with the error policy "raise" the batch raises if ANY state fails: then the reference's loop must fail somewhere too
+        for st in states:
+            try:
+                _quiet(ref.set_aircraft_state, state=copy.deepcopy(st), aircraft=name)
+                _quiet(ref.solve_forces)
+            except Exception as r:              # noqa: BLE001
+                return [] if type(r).__name__ == type(e).__name__ else ["sweep: batch raised %r, reference %r" % (e, r)]
+        return ["solve_forces_batch raised %r, the reference's loop ran through" % (e,)]
     for i, st in enumerate(states):
         try:
             _quiet(ref.set_aircraft_state, state=copy.deepcopy(st), aircraft=name)
@@ -494,6 +533,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--solve-every", type=int, default=4)
     ap.add_argument("--drivers-every", type=int, default=0)
+    ap.add_argument("--database", action="store_true", help="every case uses synthetic table look-up (database) airfoils")
     ap.add_argument("--sessions", type=int, default=0, help="session mode: that many random call sequences instead of single cases")
     ap.add_argument("--session-length", type=int, default=12)
     ap.add_argument("--keep", default=None)
@@ -503,9 +543,11 @@ def main():
     if args.sessions:
         return main_sessions(args)
     bad, rejected, solved, kept, crashed, drivers = 0, 0, 0, [], 0, 0
+    import tempfile
+    scratch = tempfile.mkdtemp(prefix="fuzz_db_") if args.database else None
     for k in range(args.cases):
         seed = args.seed + k
-        case = make_case(seed)
+        case = make_case(seed, scratch)
         solve = args.solve_every > 0 and k % args.solve_every == 0
         issues, record = compare(case, solve)
         rejected += record.get("rejected") is not None and not record.get("reference_crashed")
@@ -518,7 +560,7 @@ def main():
         if issues:
             bad += 1
             print("seed %d: %s" % (seed, "; ".join(issues)))
-        elif args.keep and record.get("rejected") is None and "FM" in record and (
+        elif args.keep and not args.database and record.get("rejected") is None and "FM" in record and (
                 len(kept) < args.keep_count or ("drivers" in record and sum("drivers" in c["reference"] for c in kept) < args.keep_drivers)):
             kept.append({"seed": seed, "input": case, "reference": record})
     print("%d cases, %d with mismatches, %d rejected by both, %d where only the reference crashed (unvalidated input), %d solved and compared, "

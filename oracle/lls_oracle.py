@@ -65,6 +65,7 @@ class Tables:
         self.afa = itab[L.I_AFA, :n].astype(np.int64)
         self.afb = itab[L.I_AFB, :n].astype(np.int64)
         self.n_segments = int(tables["n_segments"])
+        self.section_bounds = False     # set by the section model when a database airfoil is asked for a point outside its table
         self.swept = bool(self.flags & L.FLAG_SWEPT_SECTIONS)
         self.total_velocity = bool(self.flags & L.FLAG_TOTAL_VELOCITY)
         self.in_plane = bool(self.flags & L.FLAG_IN_PLANE)
@@ -262,9 +263,9 @@ def _db_record(T, a):
     return kinds, lim, vals, simp[:, :V + 1].astype(np.int64), simp[:, V + 1:V + 1 + V * V].reshape(S, V, V), simp[:, V + 1 + V * V:]
 
 
-def _db_eval(rec, X, which):
+def _db_eval(rec, X, which, found=None):
     """Interpolated coefficient `which` at the raw points X (n, V); points outside the table extrapolate from the simplex whose
-    smallest barycentric coordinate is largest."""
+    smallest barycentric coordinate is largest (and are reported through `found`, a list that receives one bool per point)."""
     kinds, lim, vals, verts, Tinv, r = rec
     xn = (X - lim[:, 0]) / lim[:, 1]
     out = np.zeros(len(xn))
@@ -274,6 +275,8 @@ def _db_eval(rec, X, which):
         cmin = np.where(np.isnan(c).any(axis=1), -np.inf, c.min(axis=1))
         inside = np.nonzero(cmin >= -DB_EPS)[0]
         s = inside[0] if inside.size else int(np.argmax(cmin))
+        if found is not None:
+            found.append(bool(inside.size))
         out[q] = np.dot(c[s], vals[verts[s], which])
     return out
 
@@ -286,8 +289,12 @@ def _db_points(T, rec, mask, alpha, Re, M):
 def _db_one(T, a, mask, alpha, Re, M, which, dkind):
     rec = _db_record(T, a)
     X = _db_points(T, rec, mask, alpha, Re, M)
-    if dkind is None:
-        return _db_eval(rec, X, which)
+    if dkind is None:           # CL, CD, Cm themselves: a point outside the table is what LLS_STATUS_SECTION_BOUNDS reports
+        found = []
+        out = _db_eval(rec, X, which, found)
+        if not all(found):
+            T.section_bounds = True
+        return out
     if dkind not in rec[0]:
         return np.zeros(mask.sum())
     v = rec[0].index(dkind)
@@ -739,5 +746,5 @@ def solve(T, solver_type="nonlinear", convergence=1e-10, relaxation=1.0, max_ite
         gamma, it, err, ok, hist = solve_nonlinear(T, F, V, gamma_lin, convergence, relaxation, max_iterations)
         out.update(iterations=it, error=err, converged=ok, history=hist)
     seg, D = integrate(T, F, V, gamma)
-    out.update(gamma=gamma, seg_fm=seg, dist=D)
+    out.update(gamma=gamma, seg_fm=seg, dist=D, section_bounds=T.section_bounds)
     return out

@@ -12,6 +12,8 @@ def _solve(tables, ac_state, solver_type, convergence, relaxation, max_iteration
     T = O.Tables(tables, ac_state)
     res = O.solve(T, solver_type=solver_type, convergence=convergence, relaxation=relaxation, max_iterations=max_iterations)
     status = 0 if res["converged"] else L.STATUS_NOT_CONVERGED
+    if res.get("section_bounds"):
+        status |= L.STATUS_SECTION_BOUNDS
     return res, status
 
 
@@ -64,16 +66,22 @@ class OracleDeviceScene:
                                                          max_iterations)
             seg, D = O.integrate(T, F, V, gamma)
             self._res = {"flow": F, "V": V, "gamma": gamma, "iterations": it, "error": err, "converged": ok, "history": hist,
-                         "seg_fm": seg, "dist": D}
-            status = 0 if ok else L.STATUS_NOT_CONVERGED
+                         "seg_fm": seg, "dist": D, "section_bounds": T.section_bounds}
+            status = (0 if ok else L.STATUS_NOT_CONVERGED) | (L.STATUS_SECTION_BOUNDS if T.section_bounds else 0)
         return self._res["iterations"], self._res["error"], status, list(self._res["history"])
 
     def integrate(self):
         if self._solver[0] != "nonlinear":
-            self._res, _ = _solve(self.tables, self.ac, "linear", 1e-10, 1.0, 1)
+            self._res, self.last_status = _solve(self.tables, self.ac, "linear", 1e-10, 1.0, 1)
+        else:
+            self.last_status = L.STATUS_SECTION_BOUNDS if self._res.get("section_bounds") else 0
         return np.array(self._res["seg_fm"], copy=True)
 
     def status(self):
+        if self._solver[0] != "nonlinear":       # the flow state and the linear solve have evaluated CL at the freestream angle
+            T = O.Tables(self.tables, self.ac)
+            O.flow_state(T)
+            return L.STATUS_SECTION_BOUNDS if T.section_bounds else 0
         return 0
 
     def out(self):
