@@ -385,6 +385,13 @@ def _same(a, b, tol, path, issues):
         for k in a:
             _same(a[k], b[k], tol, path + "/" + str(k), issues)
         return
+    if isinstance(a, (list, tuple)) and any(isinstance(v, (dict, list, tuple)) for v in a):        # e.g. (state, control_state)
+        if not isinstance(b, (list, tuple)) or len(a) != len(b):
+            issues.append("%s: sequence length" % path)
+            return
+        for i, (u, v) in enumerate(zip(a, b)):
+            _same(u, v, tol, path + "[%d]" % i, issues)
+        return
     x, y = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     if x.shape != y.shape:
         issues.append("%s: shape %s vs %s" % (path, x.shape, y.shape))
@@ -588,7 +595,7 @@ def _session_ops(rng, case, length):
         name = str(rng.choice(names))
         controls = list(case["scene"]["aircraft"][name]["file"].get("controls", {}))
         kind = rng.choice(["state", "state", "controls", "solve", "solve", "solve", "stability", "control_derivs", "aero_center",
-                           "target_CL", "pitch_trim", "distributions", "max_length"])
+                           "target_CL", "pitch_trim", "pitch_trim_orientation", "distributions", "max_length"])
         if kind == "state":
             st, _ = _state(rng, controls)
             ops.append(("set_aircraft_state", {"state": st, "aircraft": name}))
@@ -612,6 +619,9 @@ def _session_ops(rng, case, length):
                                       "batched": use_batched and bool(rng.random() < 0.7)}))
         elif kind == "pitch_trim":
             ops.append(("pitch_trim", {"aircraft": name, "set_trim_state": bool(rng.random() < 0.5), "batched": use_batched and bool(rng.random() < 0.7)}))
+        elif kind == "pitch_trim_orientation":
+            ops.append(("pitch_trim_using_orientation", {"aircraft": name, "set_trim_state": bool(rng.random() < 0.5),
+                                                         "batched": use_batched and bool(rng.random() < 0.7)}))
         elif kind == "distributions":
             ops.append(("distributions", {}))
         else:
