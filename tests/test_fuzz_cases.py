@@ -101,3 +101,42 @@ def test_fuzz_case_drivers_against_the_reference(monkeypatch, k, batched):
             scene = Scene(copy.deepcopy(case))                        # a fresh scene per driver, as when the fixture was made
             got = getattr(scene, method)(**({"batched": True} if batched else {}))
         _same(ref[method], got, tol, method)
+
+
+# ---- sessions: random SEQUENCES of calls on one scene (oracle/fuzz_host_mirror.py --sessions N --keep tests/golden/fuzz_sessions.json) ----
+with open(os.path.join(HERE, "golden", "fuzz_sessions.json")) as fh:
+    SESSIONS = json.load(fh)["sessions"]
+
+
+@pytest.mark.parametrize("k", range(len(SESSIONS)), ids=["session%d" % s["seed"] for s in SESSIONS])
+def test_fuzz_session_against_the_reference(monkeypatch, k):
+    """State changes, solves (initial_guess="previous" in the sequential sessions) and drivers (batched in the others) applied to
+    ONE scene, every answer compared with what the unmodified reference gave for the same sequence: what this protects is the
+    mirror's bookkeeping between calls -- table revisions, row and state uploads, restoring the aircraft after a stencil."""
+    oracle_backend.install(monkeypatch)
+    from machupx_b200 import Scene
+    session = SESSIONS[k]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scene = Scene(copy.deepcopy(session["input"]))
+        for step, call in enumerate(session["calls"]):
+            got = getattr(scene, call["method"])(**copy.deepcopy(call["kwargs"]))
+            want = call["result"]
+            if want is None:
+                assert got is None, (step, call["method"])
+                continue
+            tol = 1e-9 if call["method"] in ("solve_forces", "distributions", "get_max_bound_vortex_length") else 1e-6
+            _same_seq(want, got, tol, "step %d %s" % (step, call["method"]))
+
+
+def _same_seq(want, got, tol, path):
+    if isinstance(want, list) and any(isinstance(v, (dict, list)) for v in want):      # e.g. (state, control_state) of a trim
+        assert len(want) == len(got), path
+        for i, (a, b) in enumerate(zip(want, got)):
+            _same_seq(a, b, tol, path + "[%d]" % i)
+    elif isinstance(want, dict):
+        assert set(want) == set(got), path
+        for key in want:
+            _same_seq(want[key], got[key], tol, path + "/" + str(key))
+    else:
+        _same(want, got, tol, path)
