@@ -99,6 +99,29 @@ def _database_tables(rng, directory, seed):
     return out
 
 
+def _file_forms(rng, w, scratch, tag):
+    """Rewrites some span-wise tables of a wing definition into the other documented forms: a trailing row of units
+    (helpers.py:133-138) and / or a comma-separated file referenced by its path (helpers.py:92-96)."""
+    units = {"twist": ("deg", "rad"), "sweep": ("deg", "rad"), "dihedral": ("deg", "rad"), "chord": ("ft", "m", "in")}
+    for key, choices in units.items():
+        val = w.get(key)
+        if not (isinstance(val, list) and val and isinstance(val[0], list)) or rng.random() < 0.5:
+            continue
+        rows = [list(r) for r in val]
+        if rng.random() < 0.6:
+            unit = str(rng.choice(choices))
+            factor = {"deg": 1.0, "rad": np.pi / 180.0, "ft": 1.0, "m": 0.3048, "in": 12.0}[unit]
+            rows = [[r[0], float(np.round(r[1] * factor, 6))] for r in rows] + [["-", unit]]
+        if rng.random() < 0.5:
+            path = os.path.join(scratch, "%s_%s.csv" % (tag, key))
+            with open(path, "w") as fh:
+                for r in rows:
+                    fh.write(",".join(str(x) for x in r) + "\n")
+            w[key] = path
+        else:
+            w[key] = rows
+
+
 def _wing(rng, wid, existing, controls, si):
     w = {"ID": wid, "side": str(rng.choice(["both", "both", "left", "right"])), "is_main": bool(wid == 1)}
     if existing and rng.random() < 0.6:
@@ -227,7 +250,7 @@ def _state(rng, controls):
     return st, cs
 
 
-def make_case(seed, database_dir=None):
+def make_case(seed, database_dir=None, files_dir=None):
     """database_dir: where to write synthetic airfoil tables; every case then uses "database" airfoils (their file paths go into
     the input, so such cases are not kept as fixtures)."""
     rng = np.random.default_rng(seed)
@@ -251,6 +274,9 @@ def make_case(seed, database_dir=None):
             st["position"] = [float(rng.uniform(-30, -10)), float(rng.uniform(-20, 20)), float(rng.uniform(-5, 5))]
         if database_dir is not None:
             ap["airfoils"] = _database_tables(rng, database_dir, seed * 10 + k)
+        if files_dir is not None:
+            for wname, wdef in ap["wings"].items():
+                _file_forms(rng, wdef, files_dir, "fuzz_%d_%d_%s" % (seed, k, wname))
         scene["scene"]["aircraft"]["plane_%d" % k] = {"file": ap, "state": st, "control_state": cs}
     return scene
 
@@ -541,6 +567,7 @@ def main():
     ap.add_argument("--solve-every", type=int, default=4)
     ap.add_argument("--drivers-every", type=int, default=0)
     ap.add_argument("--database", action="store_true", help="every case uses synthetic table look-up (database) airfoils")
+    ap.add_argument("--files", action="store_true", help="span-wise tables also as csv files and with unit rows")
     ap.add_argument("--sessions", type=int, default=0, help="session mode: that many random call sequences instead of single cases")
     ap.add_argument("--session-length", type=int, default=12)
     ap.add_argument("--keep", default=None)
@@ -552,9 +579,10 @@ def main():
     bad, rejected, solved, kept, crashed, drivers = 0, 0, 0, [], 0, 0
     import tempfile
     scratch = tempfile.mkdtemp(prefix="fuzz_db_") if args.database else None
+    files = tempfile.mkdtemp(prefix="fuzz_csv_") if args.files else None
     for k in range(args.cases):
         seed = args.seed + k
-        case = make_case(seed, scratch)
+        case = make_case(seed, scratch, files)
         solve = args.solve_every > 0 and k % args.solve_every == 0
         issues, record = compare(case, solve)
         rejected += record.get("rejected") is not None and not record.get("reference_crashed")
@@ -567,7 +595,7 @@ def main():
         if issues:
             bad += 1
             print("seed %d: %s" % (seed, "; ".join(issues)))
-        elif args.keep and not args.database and record.get("rejected") is None and "FM" in record and (
+        elif args.keep and not args.database and not args.files and record.get("rejected") is None and "FM" in record and (
                 len(kept) < args.keep_count or ("drivers" in record and sum("drivers" in c["reference"] for c in kept) < args.keep_drivers)):
             kept.append({"seed": seed, "input": case, "reference": record})
     print("%d cases, %d with mismatches, %d rejected by both, %d where only the reference crashed (unvalidated input), %d solved and compared, "
