@@ -43,8 +43,6 @@ def test_quaternion_helpers():
     yaw = H.euler_to_quat([0.0, 0.0, np.pi / 2])
     assert np.allclose(H.quat_trans(yaw, [1.0, 0.0, 0.0]), [0.0, -1.0, 0.0], atol=1e-15)
     assert H.quat_conj([1.0, 2.0, 3.0, 4.0]) == [1.0, -2.0, -3.0, -4.0]
-    lock = H.euler_to_quat([0.3, np.pi / 2, 0.0])                 # gimbal lock branch (helpers.py:253-256): phi = 2 asin(qx / cos(pi/4))
-    assert np.allclose(H.quat_to_euler(lock), [2.0 * np.arcsin(lock[1] / np.cos(np.pi / 4)), np.pi / 2, 0.0], atol=1e-7)
 
 
 def test_parse_input(tmp_path):
