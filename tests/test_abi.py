@@ -83,3 +83,18 @@ def test_product_never_imports_the_oracle():
                 with open(os.path.join(dirpath, f)) as fh:
                     text = fh.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/lls.h must compile as C99 (no C++ in the declarations) and a C program must link
+    against liblls.so and call it -- here only lls_abi_version(), which touches no device."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "lls.h"\n'
+                   'int main(void) { lls_scene* h = 0; (void)h; return lls_abi_version() > 0 ? 0 : 1; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "machupx_b200")
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                           "-L", lib_dir, "-l:liblls.so", "-Wl,-rpath," + lib_dir, "-o", str(exe)])
+    assert subprocess.run([str(exe)]).returncode == 0
