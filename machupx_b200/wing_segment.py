@@ -88,6 +88,21 @@ def _distribution(data, angular=False, negate=False):
     return fn, fn.table
 
 
+# Quadratures of the sweep / dihedral integrands, shared by every wing segment of the process whose sweep and dihedral inputs are
+# the same numbers on the same side (the 64 identical aircraft of a swarm ask for the same 10^4 integrals 64 times).  The memo
+# returns the very floats scipy produced the first time, so the geometry stays bit-identical; callables are never memoised.
+_QUAD_MEMO = {}
+_QUAD_MEMO_LIMIT = 400000
+
+
+def _memo_key(data, negate):
+    if isinstance(data, float):
+        return ("c", data, bool(negate))
+    if isinstance(data, np.ndarray):
+        return ("t", data.shape, data.tobytes(), bool(negate))
+    return None
+
+
 def _as_span_array(span):
     return np.asarray(span, dtype=float)[np.newaxis] if isinstance(span, float) else np.asarray(span)
 
@@ -288,6 +303,9 @@ class WingSegment:
                     self._discont.append(end)
             self._discont = sorted(self._discont)
             self._interval_cache = {}
+            ks = None if callable(sweep) else _memo_key(self._getter_data["sweep"], self.side == "left")
+            kd = None if callable(dihedral) else _memo_key(self._getter_data["dihedral"], self.side == "right")
+            self._quad_key = None if ks is None or kd is None else (ks, kd)
 
         chord = read_value("chord", d, us, 1.0)
         if isinstance(chord, tuple):
@@ -340,11 +358,23 @@ class WingSegment:
         key = (lo, hi)
         hit = self._interval_cache.get(key)
         if hit is None:
+            hit = self._quad3(lo, hi)
+            self._interval_cache[key] = hit
+        return hit
+
+    def _quad3(self, lo, hi):
+        """The three integrals over [lo, hi] (process-wide memo, see _QUAD_MEMO)."""
+        key = None if self._quad_key is None else (self._quad_key, lo, hi)
+        hit = _QUAD_MEMO.get(key) if key is not None else None
+        if hit is None:
             hit = np.array([
                 integ.quad(lambda s: np.tan(self.get_sweep(s)), lo, hi)[0],
                 integ.quad(lambda s: -np.cos(self.get_dihedral(s)), lo, hi)[0],
                 integ.quad(lambda s: -np.sin(self.get_dihedral(s)), lo, hi)[0]])
-            self._interval_cache[key] = hit
+            if key is not None:
+                if len(_QUAD_MEMO) >= _QUAD_MEMO_LIMIT:
+                    _QUAD_MEMO.clear()
+                _QUAD_MEMO[key] = hit
         return hit
 
     def _get_quarter_chord_loc(self, span):
@@ -359,10 +389,8 @@ class WingSegment:
                     if s > brk[j]:
                         offset[i] += self._interval(brk[j - 1], brk[j]) * self.b
                     else:
-                        # not cached: each station has its own upper limit
-                        offset[i, 0] += integ.quad(lambda t: np.tan(self.get_sweep(t)), brk[j - 1], s)[0] * self.b
-                        offset[i, 1] += integ.quad(lambda t: -np.cos(self.get_dihedral(t)), brk[j - 1], s)[0] * self.b
-                        offset[i, 2] += integ.quad(lambda t: -np.sin(self.get_dihedral(t)), brk[j - 1], s)[0] * self.b
+                        # each station has its own upper limit: not in the per-segment cache, but shared between equal segments
+                        offset[i] += self._quad3(brk[j - 1], s) * self.b
                         break
             loc = self.get_root_loc() + offset if self.side == "left" else self.get_root_loc() - offset
         else:
