@@ -117,8 +117,12 @@ class Scene:
         self._get_viscosity = self._initialize_viscosity_getter(**atmos)
         self._get_sos = self._initialize_sos_getter(**atmos)
 
-        for key, spec in scene_dict.get("aircraft", {}).items():
-            self.add_aircraft(key, spec["file"], state=spec.get("state", {}), control_state=spec.get("control_state", {}))
+        # the scene-wide tables are built once, after the last aircraft of the input (the reference rebuilds its N x N arrays after
+        # every single one, scene.py:108-111 -> 299-301; with 64 aircraft that is 64 table builds for one scene)
+        aircraft = list(scene_dict.get("aircraft", {}).items())
+        for k, (key, spec) in enumerate(aircraft):
+            self.add_aircraft(key, spec["file"], state=spec.get("state", {}), control_state=spec.get("control_state", {}),
+                              _refresh=(k == len(aircraft) - 1))
 
     # -- atmosphere getters (scene.py:114-265): constant, "standard", altitude profile or scattered field ------------
     def _initialize_density_getter(self, **kwargs):
@@ -195,7 +199,7 @@ class Scene:
     # ------------------------------------------------------------------------------------------------------
     # aircraft management
     # ------------------------------------------------------------------------------------------------------
-    def add_aircraft(self, airplane_name, airplane_input, state={}, control_state={}):
+    def add_aircraft(self, airplane_name, airplane_input, state={}, control_state={}, _refresh=True):
         position = np.array(state.get("position", [0.0, 0.0, 0.0]))           # scene.py:287-301
         v_wind = self._get_wind(position)
         # Re-adding a name REPLACES that aircraft (the reference's own tests do it, test_airfoil_interpolation.py:139-142).  The
@@ -210,8 +214,9 @@ class Scene:
                                                   init_control_state=control_state, v_wind=v_wind)
         self._N += self._airplanes[airplane_name].N
         self._num_aircraft += 1
-        self._store_aircraft_properties()
-        self._perform_geometry_and_atmos_calcs()
+        if _refresh:
+            self._store_aircraft_properties()
+            self._perform_geometry_and_atmos_calcs()
 
     def remove_aircraft(self, airplane_name):
         try:
