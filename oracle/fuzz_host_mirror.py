@@ -400,6 +400,18 @@ def compare(case, solve):
             if not (worst[0] <= 1e-9 * scale):
                 issues.append("FM %s differs by %.3e (scale %.3e)" % (worst[1], worst[0], scale))
             record["FM"] = rf
+            # the per-control-point arrays other code reads after a solve: rows of the device's result table
+            for attr in ("_gamma", "_v_i", "_alpha", "_CL", "_Cm", "_CD", "_aL0", "_Re", "_M", "_dF_inv", "_dF_visc", "_dM_inv", "_dM_visc",
+                         "_redim_full", "_u_trailing_0", "_u_trailing_1", "_V_i_2") + (("_redim_in_plane",) if ref._use_in_plane else ()):
+                a, b = np.asarray(getattr(ref, attr), dtype=float), np.asarray(getattr(mir, attr), dtype=float)
+                if a.shape != b.shape:
+                    issues.append("%s: shape %s vs %s" % (attr, a.shape, b.shape))
+                    continue
+                fin = np.isfinite(a) & np.isfinite(b)
+                if not np.array_equal(np.isfinite(a), np.isfinite(b)):
+                    issues.append("%s: non-finite entries differ" % attr)
+                elif fin.any() and not (np.abs(a[fin] - b[fin]).max() <= 1e-9 * max(1.0, np.abs(a[fin]).max())):
+                    issues.append("%s differs by %.3e (scale %.3e)" % (attr, np.abs(a[fin] - b[fin]).max(), np.abs(a[fin]).max()))
     return issues, record
 
 
