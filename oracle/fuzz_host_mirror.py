@@ -634,6 +634,15 @@ def _session_ops(rng, case, length):
     for _ in range(length):
         name = str(rng.choice(names))
         controls = list(case["scene"]["aircraft"][name]["file"].get("controls", {}))
+        if len(names) > 1 and rng.random() < 0.12:         # take an aircraft out of the scene and put it back in another state
+            spec = case["scene"]["aircraft"][name]
+            st, cs = _state(rng, controls := list(spec["file"].get("controls", {})))
+            st["position"] = [float(rng.uniform(-40, -10)), float(rng.uniform(-20, 20)), float(rng.uniform(-5, 5))]
+            ops.append(("remove_aircraft", {"airplane_name": name}))
+            ops.append(("solve_forces", {}))
+            ops.append(("add_aircraft", {"airplane_name": name, "airplane_input": spec["file"], "state": st, "control_state": cs}))
+            ops.append(("solve_forces", {"report_by_segment": True}))
+            continue
         kind = rng.choice(["state", "state", "controls", "solve", "solve", "solve", "stability", "control_derivs", "aero_center",
                            "target_CL", "pitch_trim", "pitch_trim_orientation", "distributions", "max_length"])
         if kind == "state":
@@ -691,7 +700,7 @@ def run_session(seed, length, record=None):
             got, m_err = _quiet(getattr(mir, method), **copy.deepcopy(kw)), None
         except Exception as e:                  # noqa: BLE001
             got, m_err = None, e
-        label = "step %d %s(%s)" % (step, method, ", ".join("%s=%r" % kv for kv in kw.items() if kv[0] not in ("state", "control_state")))
+        label = "step %d %s(%s)" % (step, method, ", ".join("%s=%r" % kv for kv in kw.items() if kv[0] not in ("state", "control_state", "airplane_input")))
         if r_err is not None or m_err is not None:
             if isinstance(r_err, (UnboundLocalError, IndexError, KeyError, TypeError, AttributeError)) and m_err is None:
                 break                            # the reference tripped over its own code (e.g. pitch_trim's `alpha1`, scene.py:2560): no verdict
