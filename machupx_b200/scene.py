@@ -370,17 +370,26 @@ class Scene:
             if self._solver_type == "nonlinear":
                 if verbose: print("Running nonlinear solver...")
                 t1 = time.time()
-                its, err, status, hist = dev.solve_nonlinear(self._solver_convergence, self._solver_relaxation,
-                                                             self._max_solver_iterations)
+                try:
+                    its, err, status, hist = dev.solve_nonlinear(self._solver_convergence, self._solver_relaxation,
+                                                                 self._max_solver_iterations)
+                except KeyboardInterrupt:
+                    # scene.py:1486-1489: Ctrl-C during the Newton iteration moves on to the integration with the circulation
+                    # reached so far.  The device loop is one library call, so the interrupt is delivered when it returns:
+                    # what "so far" means here is the finished (or iteration-capped) solve.
+                    print("")
+                    print("!!! Nonlinear solver interrupted by Ctrl+C event. Moving on to force and moment integration...")
+                    its = err = hist = None
                 nonlinear_time = time.time() - t1
                 self._last_iterations, self._last_error, self._error_history = its, err, hist
-                if verbose:
-                    print("{0:<20}{1:<20}".format("Iteration", "Error"))
-                    print("".join(["-"] * 40))
-                    for k, e in enumerate(hist):
-                        print("{0:<20}{1:<20}".format(k + 1, e))
-                self._report_status(status, err)
-                if verbose: print("Nonlinear solver successfully converged. Final error: {0}".format(err))
+                if hist is not None:
+                    if verbose:
+                        print("{0:<20}{1:<20}".format("Iteration", "Error"))
+                        print("".join(["-"] * 40))
+                        for k, e in enumerate(hist):
+                            print("{0:<20}{1:<20}".format(k + 1, e))
+                    self._report_status(status, err)
+                    if verbose: print("Nonlinear solver successfully converged. Final error: {0}".format(err))
             else:
                 status = dev.status()
                 self._report_status(status, 0.0)
