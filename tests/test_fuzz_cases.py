@@ -140,3 +140,22 @@ def _same_seq(want, got, tol, path):
             _same_seq(want[key], got[key], tol, path + "/" + str(key))
     else:
         _same(want, got, tol, path)
+
+
+# ---- the same single cases on the CUDA path --------------------------------------------------------------------------------------
+# Opt-in (LLS_FUZZ_ON_GPU=1): the fixture was generated after the round's GPU minutes were spent, so this replay has never run on a
+# B200; it is kept out of the default `-m gpu` run rather than shipped unverified.
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("LLS_FUZZ_ON_GPU") != "1", reason="opt-in: set LLS_FUZZ_ON_GPU=1 (never run on a GPU yet)")
+@pytest.mark.parametrize("k", [k for k, c in enumerate(CASES) if not c["reference"].get("non_finite")],
+                         ids=["seed%d" % c["seed"] for c in CASES if not c["reference"].get("non_finite")])
+def test_fuzz_case_on_the_device(k):
+    from machupx_b200 import Scene
+    case, ref = CASES[k]["input"], CASES[k]["reference"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = _flatten(Scene(copy.deepcopy(case)).solve_forces(report_by_segment=True, stab_frame=True))
+    want = _flatten(ref["FM"])
+    assert set(got) == set(want)
+    scale = max([1.0] + [abs(v) for v in want.values()])
+    assert max(abs(got[key] - want[key]) for key in want) <= 1e-9 * scale
