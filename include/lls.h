@@ -150,7 +150,7 @@ enum lls_out_field {
     LLS_O_GAMMA = 0,   /* circulation (scene.py:827, 899)                                     */
     LLS_O_VI = 1,      /* 3: local velocity v_i (scene.py:728)                                */
     LLS_O_ALPHA = 4,   /* section angle of attack (scene.py:753, 957)                         */
-    LLS_O_CL = 5,      /* section CL incl. sweep correction (scene.py:766, 797)               */
+    LLS_O_CL = 5,      /* section CL incl. sweep correction: of the last residual evaluation (scene.py:766, 797), or, after a linear solve only, the flow-state estimate at alpha_inf (scene.py:659-666) */
     LLS_O_CD = 6,      /* section CD (scene.py:1015)                                          */
     LLS_O_CM = 7,      /* section Cm / cos(sweep) (scene.py:1020, 1026)                       */
     LLS_O_RE = 8,      /* Reynolds number (scene.py:977)                                      */
