@@ -140,7 +140,13 @@ class Scene:
                 return lambda position: np.interp(-np.transpose(position)[2], self._density_data[:, 0], self._density_data[:, 1])
             if rho.shape[1] == 4:
                 self._density_field_interpolator = sinterp.LinearNDInterpolator(rho[:, :3], rho[:, 3])
-                return lambda position: self._density_field_interpolator(position)
+
+                def field(position):
+                    # scipy answers a single point with an array of shape (1,); the reference passes that on, so that every
+                    # coefficient of its result dictionary becomes a one-element array.  A single point gets a scalar here.
+                    out = self._density_field_interpolator(position)
+                    return out.item() if np.ndim(position) == 1 else out
+                return field
         raise IOError("Density improperly specified as {0}.".format(rho))
 
     def _initialize_wind_getter(self, **kwargs):

@@ -726,6 +726,11 @@ def run_session(seed, length, record=None):
         record.update(seed=seed, input=case, calls=[])
     for step, (method, kw) in enumerate(ops):
         kr = {k: v for k, v in kw.items() if k != "batched"}
+        if method == "distributions":
+            # Scene.set_aircraft_state of the reference leaves `_solved` set unless position or orientation changed
+            # (scene.py:1560-1571), so its distributions() would report the PREVIOUS state's solve after a velocity-only change; the
+            # mirror solves the state it has.  The flag is cleared from outside to compare like with like.
+            ref._solved = False
         try:
             want, r_err = _quiet(getattr(ref, method), **copy.deepcopy(kr)), None
         except Exception as e:                  # noqa: BLE001
