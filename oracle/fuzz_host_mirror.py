@@ -599,6 +599,8 @@ def compare_sweep(case, nstates=6):
 def _jsonable(x):
     if isinstance(x, dict):
         return {str(k): _jsonable(v) for k, v in x.items()}
+    if isinstance(x, np.ndarray) and x.shape == (1,):
+        return x.item()              # the reference's one-element arrays (density field) are scalars in the fixture
     if isinstance(x, (list, tuple, np.ndarray)):
         return [_jsonable(v) for v in x]
     if isinstance(x, (np.floating, np.integer)):
@@ -648,7 +650,7 @@ def main():
           "%d with their drivers compared" % (args.cases, bad, rejected, crashed, solved, drivers))
     if args.keep:
         with open(args.keep, "w") as fh:
-            json.dump({"generator": "oracle/fuzz_host_mirror.py --seed %d" % args.seed, "cases": kept}, fh)
+            json.dump(_jsonable({"generator": "oracle/fuzz_host_mirror.py --seed %d" % args.seed, "cases": kept}), fh)
         print("kept %d cases in %s" % (len(kept), args.keep))
     return 1 if bad else 0
 
