@@ -759,7 +759,7 @@ def run_session(seed, length, record=None):
         if want is None and got is None:
             continue
         if method in ("pitch_trim", "pitch_trim_using_orientation", "target_CL"):
-            flat = _flatten(want) if isinstance(want, dict) else ({"value": float(want)} if np.isscalar(want) else {})
+            flat = _flatten(want) if isinstance(want, dict) else ({"value": float(np.ravel(want)[0])} if np.size(want) == 1 else {})
             if any(isinstance(v, (int, float)) and abs(v) > 60.0 for v in flat.values()):
                 break        # a "trim" at hundreds of degrees: the iteration wandered off and landed somewhere by chance -- no verdict
         before = len(issues)
