@@ -250,7 +250,25 @@ def _state(rng, controls):
     return st, cs
 
 
-def make_case(seed, database_dir=None, files_dir=None):
+def _callable_forms(rng, w):
+    """Span-wise inputs as Python functions of the span fraction (angles in radians), the form a script importing the package may
+    use (creating_input_files.md:286)."""
+    if "quarter_chord_locs" in w:
+        return
+    a, b = float(rng.uniform(-3, 3)), float(rng.uniform(-4, 4))
+    form = int(rng.integers(0, 4))
+    if form == 0:
+        w["twist"] = lambda s, a=a, b=b: np.radians(a + b * s)
+    elif form == 1:
+        w["chord"] = lambda s, a=a: 1.0 + 0.1 * a * s
+    elif form == 2:
+        w["dihedral"] = lambda s, a=a, b=b: np.radians(a + b * s * s)
+    else:
+        w["sweep"] = lambda s, a=a, b=b: np.radians(5 * a + 3 * b * s)
+        w.pop("ll_offset", None)        # Kuchemann's offset needs a constant sweep
+
+
+def make_case(seed, database_dir=None, files_dir=None, callables=False):
     """database_dir: where to write synthetic airfoil tables; every case then uses "database" airfoils (their file paths go into
     the input, so such cases are not kept as fixtures)."""
     rng = np.random.default_rng(seed)
@@ -291,6 +309,9 @@ def make_case(seed, database_dir=None, files_dir=None):
         if files_dir is not None:
             for wname, wdef in ap["wings"].items():
                 _file_forms(rng, wdef, files_dir, "fuzz_%d_%d_%s" % (seed, k, wname))
+        if callables:
+            for wdef in ap["wings"].values():
+                _callable_forms(rng, wdef)
         scene["scene"]["aircraft"]["plane_%d" % k] = {"file": ap, "state": st, "control_state": cs}
     return scene
 
@@ -336,7 +357,7 @@ def compare(case, solve):
         return issues, {"rejected": type(ref_error).__name__ if ref_error is not None else type(mir_error).__name__,
                         "reference_crashed": bool(crashed)}
     record = {"rejected": None}
-    database = '"database"' in json.dumps(case)
+    database = '"database"' in json.dumps(case, default=str)
     mt = mir._tables
     if database:        # the stand-in's database airfoils have no parameter block to flatten; the solves below compare them
         rt = dict(mt)
@@ -616,6 +637,7 @@ def main():
     ap.add_argument("--drivers-every", type=int, default=0)
     ap.add_argument("--database", action="store_true", help="every case uses synthetic table look-up (database) airfoils")
     ap.add_argument("--files", action="store_true", help="span-wise tables also as csv files and with unit rows")
+    ap.add_argument("--callables", action="store_true", help="span-wise inputs also as Python functions")
     ap.add_argument("--sessions", type=int, default=0, help="session mode: that many random call sequences instead of single cases")
     ap.add_argument("--session-length", type=int, default=12)
     ap.add_argument("--keep", default=None)
@@ -630,7 +652,7 @@ def main():
     files = tempfile.mkdtemp(prefix="fuzz_csv_") if args.files else None
     for k in range(args.cases):
         seed = args.seed + k
-        case = make_case(seed, scratch, files)
+        case = make_case(seed, scratch, files, args.callables)
         solve = args.solve_every > 0 and k % args.solve_every == 0
         issues, record = compare(case, solve)
         rejected += record.get("rejected") is not None and not record.get("reference_crashed")
@@ -643,7 +665,7 @@ def main():
         if issues:
             bad += 1
             print("seed %d: %s" % (seed, "; ".join(issues)))
-        elif args.keep and not args.database and not args.files and record.get("rejected") is None and "FM" in record and (
+        elif args.keep and not args.database and not args.files and not args.callables and record.get("rejected") is None and "FM" in record and (
                 len(kept) < args.keep_count or ("drivers" in record and sum("drivers" in c["reference"] for c in kept) < args.keep_drivers)):
             kept.append({"seed": seed, "input": case, "reference": record})
     print("%d cases, %d with mismatches, %d rejected by both, %d where only the reference crashed (unvalidated input), %d solved and compared, "
