@@ -55,14 +55,16 @@ class DatabaseBoundsError(Exception):
     """machupX/__init__.py:11.  Raised by the host getters of a "database" airfoil asked for a point outside its table; the
     device reports the same condition through LLS_STATUS_SECTION_BOUNDS (Scene error policy "database_bounds")."""
 
+    _TEXT = "The inputs to the airfoil database fell outside the bounds of available data."
+
     def __init__(self, airfoil="", exception_indices=(), inputs_dict=None):
-        self.airfoil = airfoil
+        """airfoil_db's signature (airfoil name, indices of the offending points, the inputs).  Scene raises it with one
+        argument, a ready-made text, which then is the message."""
+        text_only = bool(airfoil) and inputs_dict is None and len(exception_indices) == 0
+        self.airfoil = "" if text_only else airfoil
         self.exception_indices = exception_indices
         self.inputs_dict = inputs_dict or {}
-        known = ("", None) if inputs_dict is None and len(exception_indices) == 0 else ()
-        # Scene raises it with a ready-made text (one positional argument); the host getters pass the airfoil_db triple
-        super().__init__(airfoil if airfoil not in known and inputs_dict is None and len(exception_indices) == 0
-                         else "The inputs to the airfoil database fell outside the bounds of available data.")
+        super().__init__(airfoil if text_only else self._TEXT)
 
 
 def triangulate(points):
