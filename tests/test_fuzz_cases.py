@@ -10,7 +10,8 @@ replayed sequentially and with `batched=True` (the batched finite-difference ste
 What the fuzzer has found so far (all fixed or reproduced): a batched control stencil of an aircraft without controls crashed; a
 zero lateral reference length raised where the reference returns inf; the reference solves the angular-rate perturbations of
 `state_derivatives()` with the atmosphere of the previous position perturbation (scene.py:2383-2390; reproduced, 1.5e-5 in a
-standard atmosphere); `section_CL` after a LINEAR solve is the flow-state estimate (scene.py:659-666)."""
+standard atmosphere); `section_CL` after a LINEAR solve is the flow-state estimate (scene.py:659-666); with a density FIELD the trims
+crashed on the one-element arrays scipy's interpolator returns for a single point (a scalar now)."""
 import copy
 import json
 import os
