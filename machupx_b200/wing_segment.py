@@ -92,7 +92,7 @@ def _distribution(data, angular=False, negate=False):
 # the same numbers on the same side (the 64 identical aircraft of a swarm ask for the same 10^4 integrals 64 times).  The memo
 # returns the very floats scipy produced the first time, so the geometry stays bit-identical; callables are never memoised.
 _QUAD_MEMO = {}
-_QUAD_MEMO_LIMIT = 400000
+_QUAD_MEMO_LIMIT = 100000      # ~30 MB; cleared when full (a 64 000-point swarm of identical aircraft needs 2 000 entries)
 
 
 def _memo_key(data, negate):
